@@ -1,0 +1,215 @@
+/*
+ * sfw_b200.h — C ABI of the B200-native DWA + social-force trajectory sampler/scorer.
+ *
+ * This is the drop-in boundary for ONE path of robotics-upo/social_force_window_planner: the
+ * (v, w) sampling / scoring loop of SFWPlanner::findBestAction
+ * (reference src/sfw_planner.cpp:338-417) together with everything it calls per sample:
+ * SFWPlanner::scoreTrajectory (:475-676), SFWPlanner::computeSocialWork (:678-705),
+ * WorldModel/CostmapModel::footprintCost (include/.../world_model.hpp:45-75,
+ * src/costmap_model.cpp:21-121, include/.../line_iterator.hpp:37-124) and the lightsfm
+ * calls sfm::SFM.computeForces / updatePosition (:592, :594, :697).
+ *
+ * Plain C: pointers + sizes only, no C++/torch types.  Every entry point returns an int status
+ * (SFW_OK == 0, negative on error) and never throws.  There is NO CPU fallback: if no CUDA
+ * device is usable sfw_create fails with SFW_ERR_CUDA and nothing else can be called.
+ *
+ * Threading: one in-flight call per context (the reference holds configuration_mutex_ for the
+ * whole findBestAction, src/sfw_planner.cpp:123-454).  Contexts are independent.
+ */
+#ifndef SFW_B200_H
+#define SFW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFW_ABI_VERSION 1
+
+/* status codes */
+#define SFW_OK 0
+#define SFW_ERR_ARG (-1)         /* null pointer / inconsistent sizes */
+#define SFW_ERR_CUDA (-2)        /* CUDA runtime/driver failure; see sfw_last_error */
+#define SFW_ERR_UNSUPPORTED (-3) /* input outside what the kernels implement (see sfw_last_error) */
+#define SFW_ERR_STATE (-4)       /* call order violated (e.g. sfw_run before sfw_upload) */
+
+/* per-trajectory cost codes written to the cost vector */
+#define SFW_COST_INVALID (-1.0f) /* reference returns -1.0 on any violation (sfw_planner.cpp:546-573,624) */
+#define SFW_COST_SKIPPED (-2.0f) /* the (0,0) sample is never scored (sfw_planner.cpp:349-352) */
+
+/*
+ * ControllerParams fields that the scoring path reads (reference
+ * include/social_force_window_planner/sfw_planner.hpp:55-227; used at
+ * src/sfw_planner.cpp:356-358,519,527,617,654,663-667).  Types follow the reference
+ * (robot_radius_ is a float there, hpp:208, and is squared in float at cpp:617).
+ */
+typedef struct SfwParams {
+  double max_vel_x;       /* max_trans_vel  (0.7) */
+  double max_trans_acc;   /* max_trans_acc  (1.0) -> acc_x; acc_y is always 0 (cpp:357) */
+  double max_rot_acc;     /* max_rot_acc    (1.0) -> acc_theta */
+  double sim_time;        /* sim_time       (1.0) */
+  double sim_granularity; /* sim_granularity (0.025): num_steps = int(sim_time/gran + 0.5) (cpp:519) */
+  float robot_radius;     /* robot_radius   (0.35f): robot-pedestrian collision radius (cpp:617) */
+  float reserved0;
+  double social_weight;   /* 1.2 */
+  double costmap_weight;  /* 2.0 */
+  double angle_weight;    /* 0.7 */
+  double distance_weight; /* 1.0 */
+  double vel_weight;      /* velocity_weight 1.0 */
+} SfwParams;
+
+/*
+ * lightsfm sfm::Parameters (un-vendored dependency; defaults restated in SURVEY.md Appendix B).
+ * The reference never changes them, so one set applies to every agent of a call.
+ * Pass NULL wherever this struct is accepted to get the defaults below.
+ */
+typedef struct SfwSfmParams {
+  double force_factor_desired;         /* 2.0  */
+  double force_factor_obstacle;        /* 10.0 */
+  double force_sigma_obstacle;         /* 0.2  */
+  double force_factor_social;          /* 2.1  */
+  double force_factor_group_gaze;      /* 3.0  */
+  double force_factor_group_coherence; /* 2.0  */
+  double force_factor_group_repulsion; /* 1.0  */
+  double lambda;                       /* 2.0  */
+  double gamma;                        /* 0.35 */
+  double n;                            /* 2.0  */
+  double n_prime;                      /* 3.0  */
+  double relaxation_time;              /* 0.5  */
+} SfwSfmParams;
+
+/*
+ * Robot inputs of one scoreTrajectory sweep (src/sfw_planner.cpp:475-481).
+ * x..vtheta are the values findBestAction passes after narrowing to float (cpp:145-152): the
+ * CALLER narrows (the host shim does), the library uses them as given.
+ * agent_* is agents[0] exactly as SFMSensorInterface::getAgents returned it
+ * (src/sensor_interface.cpp:553-579,618-631): odom pose, ROBOT-frame velocity, radius.  It is the
+ * robot state the first computeForces sees (cpp:592, i == 0) before the rollout overwrites it.
+ */
+typedef struct SfwRobot {
+  double x, y, theta;             /* start pose of the rollout */
+  double vx, vy, vtheta;          /* current velocity (vy never changes: acc_y == 0) */
+  double wpx, wpy;                /* waypoint scored against (cpp:643-652) */
+  double agent_x, agent_y;        /* agents[0].position */
+  double agent_vx, agent_vy;      /* agents[0].velocity (robot frame, sensor_interface.cpp:575) */
+  double agent_radius;            /* agents[0].radius (sensor_interface.cpp:34) */
+} SfwRobot;
+
+/*
+ * One pedestrian = agents[1..P] as built by SFMSensorInterface::peopleCb
+ * (src/sensor_interface.cpp:447-504): position, velocity, one naive goal, desired speed, radius,
+ * group id.  has_goal == 0 means an empty goal list (lightsfm then brakes the agent).
+ */
+typedef struct SfwPed {
+  double x, y;
+  double vx, vy;
+  double goal_x, goal_y;
+  double goal_radius;
+  double desired_velocity;
+  double radius;
+  int32_t has_goal;
+  int32_t group_id; /* -1 = none (sensor_interface.cpp:449) */
+  int32_t id;       /* people tag id; robot id is taken as -1 */
+  int32_t reserved0;
+} SfwPed;
+
+/*
+ * One planning scene: robot + costmap + pedestrians + the obstacle points shared by all agents
+ * (sensor_interface.cpp:513-524) + footprint polygon (robot frame).  All pointers are caller
+ * owned host memory and are only read during the call.
+ * costmap: row-major uint8, cost(mx,my) = costmap[my*size_x + mx] (nav2 Costmap2D layout).
+ */
+typedef struct SfwScene {
+  SfwRobot robot;
+  const uint8_t *costmap;
+  uint32_t size_x, size_y;
+  double resolution, origin_x, origin_y;
+  const SfwPed *peds;
+  uint32_t n_peds;
+  uint32_t n_obstacles;
+  const double *obstacles_xy; /* n_obstacles pairs (x,y) */
+  const double *footprint_xy; /* n_footprint pairs (x,y), robot frame; <3 => centre-cell mode */
+  uint32_t n_footprint;
+  uint32_t reserved0;
+} SfwScene;
+
+/* Winner of one scene (reference: best_traj / vx, vt at src/sfw_planner.cpp:394-414,426-468). */
+typedef struct SfwBest {
+  int32_t valid;  /* 0 => no valid trajectory: findBestAction returns false, zero twist (cpp:456-468) */
+  uint32_t index; /* i = i_v * n_w + i_w (cpp:342-416) */
+  float cost;
+  float reserved0;
+  double v, w;    /* chosen (linvel, angvel); 0,0 when !valid */
+} SfwBest;
+
+/* Limits used to pre-size device buffers; all may be exceeded later (buffers grow). */
+typedef struct SfwLimits {
+  uint32_t max_scenes;
+  uint32_t max_samples; /* n_v * n_w */
+  uint32_t max_peds;
+  uint32_t max_obstacles;
+  uint32_t max_cells; /* size_x * size_y */
+} SfwLimits;
+
+typedef struct sfw_ctx sfw_ctx;
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+int sfw_abi_version(void);
+/* device: CUDA ordinal.  stream: a cudaStream_t to run on, or NULL for a private non-blocking
+ * stream owned by the context.  limits may be NULL. */
+int sfw_create(sfw_ctx **out, int device, void *stream, const SfwLimits *limits);
+int sfw_destroy(sfw_ctx *ctx);
+const char *sfw_last_error(const sfw_ctx *ctx); /* ctx may be NULL: last sfw_create error */
+void sfw_default_params(SfwParams *p);          /* reference header defaults (sfw_planner.hpp:56-66) */
+void sfw_default_sfm_params(SfwSfmParams *p);   /* lightsfm defaults */
+
+/* ---- the hot path --------------------------------------------------------------------------
+ * sfw_score: one scene, the whole (linvels x angvels) grid; replaces the double loop of
+ * SFWPlanner::findBestAction (src/sfw_planner.cpp:345-417).  costs_out (n_v*n_w floats, may be
+ * NULL) receives the per-trajectory cost vector, best_out the arg-min with the reference's
+ * tie-breaks.  Synchronous: host buffers are filled on return.
+ * sfw_score_batch: n_scenes independent scenes sharing params, sample arrays and array sizes
+ * (size_x/size_y/n_peds/n_obstacles/n_footprint may differ per scene up to the first scene's
+ * values being an upper bound is NOT required; the library sizes for the maximum). */
+int sfw_score(sfw_ctx *ctx, const SfwParams *params, const SfwSfmParams *sfm, const SfwScene *scene,
+              const double *linvels, uint32_t n_v, const double *angvels, uint32_t n_w,
+              float *costs_out, SfwBest *best_out);
+int sfw_score_batch(sfw_ctx *ctx, const SfwParams *params, const SfwSfmParams *sfm,
+                    const SfwScene *scenes, uint32_t n_scenes, const double *linvels, uint32_t n_v,
+                    const double *angvels, uint32_t n_w, float *costs_out, SfwBest *best_out);
+
+/* ---- split form of the same call (staging / launch / fetch), for callers that keep scenes
+ * resident on the device across ticks and for benchmarking the kernel alone ------------------ */
+int sfw_upload(sfw_ctx *ctx, const SfwParams *params, const SfwSfmParams *sfm, const SfwScene *scenes,
+               uint32_t n_scenes, const double *linvels, uint32_t n_v, const double *angvels,
+               uint32_t n_w);          /* pack + async H2D on the context stream */
+int sfw_run(sfw_ctx *ctx);             /* launch the scorer on the staged scenes (async) */
+int sfw_download(sfw_ctx *ctx, float *costs_out, SfwBest *best_out); /* D2H + stream sync */
+int sfw_sync(sfw_ctx *ctx);            /* cudaStreamSynchronize on the context stream */
+
+/* Restrict the next sfw_run calls to linvel rows [row_begin, row_end) of every staged scene
+ * (multi-GPU sharding of a single scene across ranks: each rank scores a slab and the winners
+ * are all-gathered by the caller).  Rows outside the slab get SFW_COST_SKIPPED. */
+int sfw_set_row_slab(sfw_ctx *ctx, uint32_t row_begin, uint32_t row_end);
+
+/* Winner trajectory points (Trajectory::x_pts_/y_pts_/th_pts_, src/trajectory.cpp:36-40) for one
+ * sample of one staged scene: fills up to max_points (x,y,theta) triples, returns the number of
+ * points the rollout recorded in *n_points (stops at the first illegal pose like the reference). */
+int sfw_trajectory_points(sfw_ctx *ctx, uint32_t scene, uint32_t sample_index, double *xyz_out,
+                          uint32_t max_points, uint32_t *n_points);
+
+/* ---- introspection (benchmark / interop) ---------------------------------------------------- */
+void *sfw_stream(sfw_ctx *ctx);                 /* cudaStream_t the context launches on */
+const float *sfw_device_costs(sfw_ctx *ctx);    /* device cost vector of the last run */
+const void *sfw_device_best(sfw_ctx *ctx);      /* device SfwBest[n_scenes] of the last run */
+uint64_t sfw_kernel_launches(const sfw_ctx *ctx); /* kernels launched by this context so far */
+/* algorithmic bytes of the staged batch (SURVEY.md section 8d formula) */
+uint64_t sfw_algorithmic_bytes(const sfw_ctx *ctx);
+/* name of the kernel variant the last sfw_run dispatched to (for logs/profiles) */
+const char *sfw_last_kernel(const sfw_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFW_B200_H */

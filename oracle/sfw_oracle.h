@@ -1,0 +1,80 @@
+/*
+ * sfw_oracle.h — CPU restatement (double precision, plain C) of the reference's (v,w) scoring path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it, and
+ * only as the checker or the timed CPU baseline.  The product (libsfw_b200.so) never links,
+ * loads or calls it.
+ *
+ * PARITY PINNING: the rollout / footprint / cost / arg-min logic is checked bit-for-bit against
+ * the reference's own sources compiled unmodified (oracle/_ref, built by oracle/Makefile from
+ * /root/reference/src/{sfw_planner,costmap_model,trajectory}.cpp).  The lightsfm arithmetic
+ * (desired / obstacle / social / group force, position update) is a restatement of an
+ * UN-VENDORED dependency with no pinned version (reference package.xml:31): at that boundary
+ * parity is UNPINNED — both oracle and oracle/_ref use the same restated formulas.
+ */
+#ifndef SFW_ORACLE_H
+#define SFW_ORACLE_H
+
+#include "../include/sfw_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Per-trajectory distance to the nearest discontinuity of the model, so parity tests can tell a
+ * float-vs-double rounding difference from a branch flip (goal pop, collision, sign(theta)). */
+typedef struct SfwOracleMargins {
+  double goal;      /* min over steps/peds of | |goal - p| - goal_radius |  (metres) */
+  double collision; /* min over steps/peds of | |robot - ped| - robot_radius | (metres) */
+  double theta;     /* min over non-negligible pair evaluations of |theta| (radians) */
+  double cell;      /* min distance (metres) of any rasterised world point to a cell boundary */
+} SfwOracleMargins;
+
+/* One scoreTrajectory call (reference src/sfw_planner.cpp:475-676).  pts_xyz (nullable) receives
+ * the recorded (x,y,theta) points, *n_pts their count.  Returns the cost or -1.0. */
+double sfw_oracle_score_trajectory(const SfwParams *params, const SfwSfmParams *sfm,
+                                   const SfwScene *scene, double vx_samp, double vy_samp,
+                                   double vtheta_samp, double acc_x, double acc_y, double acc_theta,
+                                   double *pts_xyz, uint32_t max_pts, uint32_t *n_pts,
+                                   SfwOracleMargins *margins);
+
+/* The double loop + arg-min of findBestAction (reference src/sfw_planner.cpp:338-417,426-468).
+ * costs_out: n_v*n_w doubles (-1 invalid, -2 skipped (0,0)); margins_out nullable. */
+int sfw_oracle_score(const SfwParams *params, const SfwSfmParams *sfm, const SfwScene *scene,
+                     const double *linvels, uint32_t n_v, const double *angvels, uint32_t n_w,
+                     double *costs_out, SfwBest *best_out, SfwOracleMargins *margins_out);
+
+/* Same cost vector, samples farmed over n_threads pthreads (timing baseline; the arg-min is
+ * re-run serially over the cost vector so the result is identical to sfw_oracle_score). */
+int sfw_oracle_score_mt(const SfwParams *params, const SfwSfmParams *sfm, const SfwScene *scene,
+                        const double *linvels, uint32_t n_v, const double *angvels, uint32_t n_w,
+                        double *costs_out, SfwBest *best_out, int n_threads);
+
+/* Arg-min of a cost vector with the reference's sequential tie-break semantics
+ * (src/sfw_planner.cpp:344,394-414). */
+void sfw_oracle_argmin(const double *costs, const double *linvels, uint32_t n_v,
+                       const double *angvels, uint32_t n_w, SfwBest *best_out);
+
+/* WorldModel::footprintCost(x,y,theta,spec) -> CostmapModel::footprintCost
+ * (world_model.hpp:45-75, costmap_model.cpp:21-92).  Returns -3/-2/-1 or the max cell cost. */
+double sfw_oracle_footprint_cost(const SfwScene *scene, double x, double y, double theta,
+                                 double *cell_margin);
+
+/* Bresenham cells of LineIterator (line_iterator.hpp:37-124): writes up to max_cells (x,y) pairs,
+ * returns the number of cells of the line. */
+int sfw_oracle_line_cells(int x0, int y0, int x1, int y1, int *cells_xy, int max_cells);
+
+/* lightsfm pair social force on `me` from `other` (restated).  Inputs are
+ * (px,py,vx,vy) each; out_fxy receives the force already scaled by forceFactorSocial. */
+void sfw_oracle_pair_force(const SfwSfmParams *sfm, const double me[4], const double other[4],
+                           double out_fxy[2], double *theta_out);
+
+/* lightsfm obstacle force on an agent at (px,py) with radius r from the scene obstacle list. */
+void sfw_oracle_obstacle_force(const SfwSfmParams *sfm, double px, double py, double radius,
+                               const double *obstacles_xy, uint32_t n_obstacles, double out_fxy[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
