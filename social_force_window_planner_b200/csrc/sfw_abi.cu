@@ -1,0 +1,794 @@
+// sfw_abi.cu — host side of the C ABI declared in include/sfw_b200.h.
+//
+// Packs caller scenes (FP64, AoS, reference-shaped: sfm::Agent / ControllerParams / Costmap2D) into
+// the device layout of sfw_dev.h inside ONE pinned arena, ships it with ONE async H2D copy on the
+// context stream, launches the scorer and brings back SfwBest (+ the cost vector on request).
+// There is no CPU scoring path in this file: every result comes from the kernels.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "sfw_dev.h"
+#include "sfw_kernels.h"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Arena {
+  uint8_t *host = nullptr; // pinned
+  uint8_t *dev = nullptr;
+  size_t cap = 0;
+};
+
+struct Plan {
+  // shape key
+  uint32_t n_scenes = 0, samples = 0, maxP = 0, maxM = 0, maxF = 0, win_bytes = 0;
+  // result
+  uint32_t T = 0, tiles = 0;
+  size_t smem = 0;
+  bool valid = false;
+};
+
+} // namespace
+
+struct sfw_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  std::string err;
+  std::mutex mu;
+
+  Arena in;   // packed inputs
+  Arena out;  // best | costs | npts | blockbest | counters
+  double *d_points = nullptr;
+  double *h_points = nullptr;
+  uint32_t points_cap = 0;
+
+  SfwBatchDev B;
+  CUtensorMap tmap;
+  bool staged = false, ran = false;
+  // tensor-map cache key
+  const void *tm_ptr = nullptr;
+  uint32_t tm_pitch = 0, tm_rows = 0, tm_scenes = 0, tm_wp = 0, tm_h = 0;
+  Plan plan;
+  size_t off_best = 0, off_costs = 0, off_npts = 0, off_bb = 0, off_cnt = 0;
+  uint32_t out_scenes = 0, out_samples = 0, out_tiles = 0;
+  uint64_t launches = 0;
+  uint64_t algo_bytes = 0;
+  size_t in_bytes = 0;
+  const char *last_kernel = "none";
+  uint32_t slab_begin = 0, slab_end = 0xffffffffu;
+  std::vector<SfwSceneDev> scene_host; // host copy for trajectory_points
+};
+
+namespace {
+
+int fail(sfw_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c)
+    c->err = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define CK(ctx, call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail((ctx), SFW_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),    \
+                  __FILE__, __LINE__);                                                             \
+  } while (0)
+
+int arena_reserve(sfw_ctx *c, Arena &a, size_t bytes) {
+  if (bytes <= a.cap)
+    return SFW_OK;
+  // the stream may still be reading the old buffers
+  CK(c, cudaStreamSynchronize(c->stream));
+  if (a.host)
+    cudaFreeHost(a.host);
+  if (a.dev)
+    cudaFree(a.dev);
+  a.host = nullptr;
+  a.dev = nullptr;
+  a.cap = 0;
+  size_t cap = align_up(bytes + bytes / 4, 1 << 16);
+  CK(c, cudaMallocHost((void **)&a.host, cap));
+  CK(c, cudaMalloc((void **)&a.dev, cap));
+  a.cap = cap;
+  return SFW_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 3-D uint8 tensor [scene][row][col] over the costmap slots; box = one scene's window.
+int make_tensor_map(sfw_ctx *c, const uint8_t *maps, uint32_t pitch, uint32_t rows, uint32_t scenes,
+                    uint32_t wp, uint32_t wh) {
+  if (c->tm_ptr == maps && c->tm_pitch == pitch && c->tm_rows == rows && c->tm_scenes == scenes &&
+      c->tm_wp == wp && c->tm_h == wh)
+    return SFW_OK;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc)
+    return fail(c, SFW_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {pitch, rows, scenes};
+  cuuint64_t strides[2] = {pitch, (cuuint64_t)pitch * rows};
+  cuuint32_t box[3] = {wp, wh, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)maps, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(c, SFW_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  c->tm_ptr = maps;
+  c->tm_pitch = pitch;
+  c->tm_rows = rows;
+  c->tm_scenes = scenes;
+  c->tm_wp = wp;
+  c->tm_h = wh;
+  return SFW_OK;
+}
+
+const SfwSfmParams kDefaultSfm = {2.0, 10.0, 0.2, 2.1, 3.0, 2.0, 1.0, 2.0, 0.35, 2.0, 3.0, 0.5};
+
+// Choose block size / tiling for the thread-per-trajectory kernel: maximise resident threads per
+// SM under the shared-memory and register limits, then shrink the block so a single-wave launch
+// is spread evenly over all SMs.
+int make_plan(sfw_ctx *c, uint32_t n_scenes, uint32_t samples, uint32_t P, uint32_t M, uint32_t F,
+              uint32_t win_bytes) {
+  Plan &pl = c->plan;
+  if (pl.valid && pl.n_scenes == n_scenes && pl.samples == samples && pl.maxP == P && pl.maxM == M &&
+      pl.maxF == F && pl.win_bytes == win_bytes)
+    return SFW_OK;
+  uint32_t bestT = 0, bestK = 0;
+  size_t max_dyn = 0;
+  CK(c, sfw_small_max_dynamic_smem(&max_dyn));
+  for (uint32_t T = SFW_MAX_BLOCK_SMALL; T >= 32; T -= 32) {
+    size_t smem = sfw_small_smem_bytes(win_bytes, P, M, F, T);
+    if (smem > max_dyn)
+      continue;
+    int k = 0;
+    CK(c, sfw_small_occupancy(T, smem, &k));
+    if (k <= 0)
+      continue;
+    if ((uint64_t)k * T > (uint64_t)bestK * bestT) {
+      bestK = (uint32_t)k;
+      bestT = T;
+    }
+  }
+  if (!bestT)
+    return fail(c, SFW_ERR_UNSUPPORTED,
+                "scene does not fit the thread-per-trajectory kernel (peds=%u obstacles=%u)", P, M);
+  const uint64_t total = (uint64_t)n_scenes * samples;
+  const uint64_t resident = (uint64_t)c->sm_count * bestK * bestT;
+  uint32_t T = bestT;
+  if (total <= resident) {
+    // single wave: spread evenly, keep the same number of blocks per SM
+    uint64_t per_block = (total + (uint64_t)c->sm_count * bestK - 1) / ((uint64_t)c->sm_count * bestK);
+    T = (uint32_t)std::min<uint64_t>(bestT, std::max<uint64_t>(32, align_up(per_block, 32)));
+  } else {
+    const uint64_t waves = (total + resident - 1) / resident;
+    uint64_t per_block = (total + waves * c->sm_count * bestK - 1) / (waves * c->sm_count * bestK);
+    T = (uint32_t)std::min<uint64_t>(bestT, std::max<uint64_t>(32, align_up(per_block, 32)));
+  }
+  if (T > samples)
+    T = (uint32_t)std::max<size_t>(32, align_up(samples, 32));
+  pl.n_scenes = n_scenes;
+  pl.samples = samples;
+  pl.maxP = P;
+  pl.maxM = M;
+  pl.maxF = F;
+  pl.win_bytes = win_bytes;
+  pl.T = T;
+  pl.tiles = (samples + T - 1) / T;
+  pl.smem = sfw_small_smem_bytes(win_bytes, P, M, F, T);
+  pl.valid = true;
+  return SFW_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int sfw_abi_version(void) { return SFW_ABI_VERSION; }
+
+void sfw_default_params(SfwParams *p) {
+  if (!p)
+    return;
+  memset(p, 0, sizeof(*p));
+  p->max_vel_x = 0.7;
+  p->max_trans_acc = 1.0;
+  p->max_rot_acc = 1.0;
+  p->sim_time = 1.0;
+  p->sim_granularity = 0.025;
+  p->robot_radius = 0.35f;
+  p->social_weight = 1.2;
+  p->costmap_weight = 2.0;
+  p->angle_weight = 0.7;
+  p->distance_weight = 1.0;
+  p->vel_weight = 1.0;
+}
+
+void sfw_default_sfm_params(SfwSfmParams *p) {
+  if (p)
+    *p = kDefaultSfm;
+}
+
+const char *sfw_last_error(const sfw_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int sfw_create(sfw_ctx **out, int device, void *stream, const SfwLimits *limits) {
+  if (!out)
+    return fail(nullptr, SFW_ERR_ARG, "sfw_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, SFW_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n)
+    return fail(nullptr, SFW_ERR_ARG, "device %d out of range (have %d)", device, n);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess)
+    return fail(nullptr, SFW_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess)
+    return fail(nullptr, SFW_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major < 10)
+    return fail(nullptr, SFW_ERR_UNSUPPORTED,
+                "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                prop.major, prop.minor);
+  sfw_ctx *c = new sfw_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  memset(&c->B, 0, sizeof(c->B));
+  memset(&c->tmap, 0, sizeof(c->tmap));
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+  } else {
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete c;
+      return fail(nullptr, SFW_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    c->own_stream = true;
+  }
+  if (limits) {
+    size_t in_est = (size_t)limits->max_scenes *
+                        (sizeof(SfwSceneDev) + (size_t)limits->max_peds * 48 +
+                         (size_t)limits->max_obstacles * 8 + 1024 + align_up(limits->max_cells, 256)) +
+                    65536;
+    size_t out_est = (size_t)limits->max_scenes * (sizeof(SfwBest) + (size_t)limits->max_samples * 6 + 4096);
+    if (arena_reserve(c, c->in, in_est) != SFW_OK || arena_reserve(c, c->out, out_est) != SFW_OK) {
+      g_create_error = c->err;
+      sfw_destroy(c);
+      return SFW_ERR_CUDA;
+    }
+  }
+  *out = c;
+  return SFW_OK;
+}
+
+int sfw_destroy(sfw_ctx *c) {
+  if (!c)
+    return SFW_OK;
+  cudaSetDevice(c->device);
+  if (c->stream)
+    cudaStreamSynchronize(c->stream);
+  if (c->in.host)
+    cudaFreeHost(c->in.host);
+  if (c->in.dev)
+    cudaFree(c->in.dev);
+  if (c->out.host)
+    cudaFreeHost(c->out.host);
+  if (c->out.dev)
+    cudaFree(c->out.dev);
+  if (c->d_points)
+    cudaFree(c->d_points);
+  if (c->h_points)
+    cudaFreeHost(c->h_points);
+  if (c->own_stream && c->stream)
+    cudaStreamDestroy(c->stream);
+  delete c;
+  return SFW_OK;
+}
+
+int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, const SfwScene *scenes,
+               uint32_t n_scenes, const double *linvels, uint32_t n_v, const double *angvels,
+               uint32_t n_w) {
+  if (!c)
+    return SFW_ERR_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!params || !scenes || !n_scenes || !linvels || !angvels || !n_v || !n_w)
+    return fail(c, SFW_ERR_ARG, "sfw_upload: null/empty argument");
+  if (!(params->sim_granularity > 0.0) || !(params->sim_time >= 0.0) || !(params->max_vel_x != 0.0))
+    return fail(c, SFW_ERR_ARG, "sfw_upload: sim_granularity must be > 0, sim_time >= 0, max_vel_x != 0");
+  if ((uint64_t)n_v * n_w > 0x7fffffffull)
+    return fail(c, SFW_ERR_ARG, "sfw_upload: too many samples");
+  CK(c, cudaSetDevice(c->device));
+  const SfwSfmParams &sfm = sfm_in ? *sfm_in : kDefaultSfm;
+  c->staged = false;
+  c->ran = false;
+
+  // ---- shape scan ------------------------------------------------------------------------------
+  uint32_t maxP = 0, maxM = 0, maxF = 0, max_sx = 0, max_sy = 0;
+  uint64_t totP = 0, totM = 0, totF = 0;
+  for (uint32_t s = 0; s < n_scenes; ++s) {
+    const SfwScene &sc = scenes[s];
+    if (!sc.costmap || !sc.size_x || !sc.size_y || !(sc.resolution > 0.0))
+      return fail(c, SFW_ERR_ARG, "scene %u: costmap missing or empty", s);
+    if ((sc.n_peds && !sc.peds) || (sc.n_obstacles && !sc.obstacles_xy) ||
+        (sc.n_footprint && !sc.footprint_xy))
+      return fail(c, SFW_ERR_ARG, "scene %u: null array with non-zero count", s);
+    if (sc.n_peds > SFW_MAX_PEDS_SMALL)
+      return fail(c, SFW_ERR_UNSUPPORTED, "scene %u: %u pedestrians > %d supported by this build", s,
+                  sc.n_peds, SFW_MAX_PEDS_SMALL);
+    if (sc.n_footprint > SFW_MAX_FOOTPRINT)
+      return fail(c, SFW_ERR_UNSUPPORTED, "scene %u: footprint with %u vertices > %d", s,
+                  sc.n_footprint, SFW_MAX_FOOTPRINT);
+    for (uint32_t j = 0; j < sc.n_peds; ++j) {
+      if (sc.peds[j].group_id >= 0) {
+        for (uint32_t k = j + 1; k < sc.n_peds; ++k)
+          if (sc.peds[k].group_id == sc.peds[j].group_id)
+            return fail(c, SFW_ERR_UNSUPPORTED,
+                        "scene %u: pedestrian groups (group_id >= 0 shared by >= 2 agents) are not "
+                        "implemented by the kernels yet",
+                        s);
+      }
+    }
+    maxP = std::max(maxP, sc.n_peds);
+    maxM = std::max(maxM, sc.n_obstacles);
+    maxF = std::max(maxF, sc.n_footprint);
+    max_sx = std::max(max_sx, sc.size_x);
+    max_sy = std::max(max_sy, sc.size_y);
+    totP += sc.n_peds;
+    totM += align_up(sc.n_obstacles, 2); // keep every scene's obstacle block 16 B aligned
+    totF += sc.n_footprint;
+  }
+
+  // ---- rollout constants --------------------------------------------------------------------
+  int num_steps = (int)(params->sim_time / params->sim_granularity + 0.5); // sfw_planner.cpp:519
+  if (num_steps == 0)
+    num_steps = 1;
+  if (num_steps > 65535)
+    return fail(c, SFW_ERR_UNSUPPORTED, "num_steps %d > 65535", num_steps);
+  const double dt = params->sim_time / num_steps; // :527
+
+  // ---- staged window: everything the footprint can touch ------------------------------------
+  double max_lin = 0.0;
+  for (uint32_t i = 0; i < n_v; ++i)
+    max_lin = std::max(max_lin, std::fabs(linvels[i]));
+  uint32_t win_wp = 0, win_h = 0;
+  std::vector<int32_t> wx0(n_scenes), wy0(n_scenes);
+  {
+    int64_t need = 0;
+    bool ok = true;
+    for (uint32_t s = 0; s < n_scenes && ok; ++s) {
+      const SfwScene &sc = scenes[s];
+      double circ = 0.0;
+      for (uint32_t k = 0; k < sc.n_footprint; ++k)
+        circ = std::max(circ, std::hypot(sc.footprint_xy[2 * k], sc.footprint_xy[2 * k + 1]));
+      const double speed = std::hypot(std::max(max_lin, std::fabs(sc.robot.vx)), sc.robot.vy);
+      const double reach = speed * params->sim_time + circ;
+      const double rc_d = std::ceil(reach / sc.resolution) + 2.0;
+      if (!(rc_d < 4096.0)) {
+        ok = false;
+        break;
+      }
+      const int64_t rc = (int64_t)rc_d;
+      const double cxd = std::floor((sc.robot.x - sc.origin_x) / sc.resolution);
+      const double cyd = std::floor((sc.robot.y - sc.origin_y) / sc.resolution);
+      if (!(std::fabs(cxd) < 1e9) || !(std::fabs(cyd) < 1e9)) {
+        ok = false;
+        break;
+      }
+      // TMA (measured on B200): the innermost start coordinate times the element size must be a
+      // multiple of 16 bytes or the copy traps as an illegal instruction -> floor x0 to 16 cells
+      // and widen the box by the slack.
+      const int64_t x0 = (int64_t)cxd - rc;
+      const int64_t x0a = (x0 >= 0) ? (x0 / 16) * 16 : -(((-x0) + 15) / 16) * 16;
+      wx0[s] = (int32_t)x0a;
+      wy0[s] = (int32_t)((int64_t)cyd - rc);
+      need = std::max<int64_t>(need, 2 * rc + 1);
+    }
+    if (ok && need > 0) {
+      const uint32_t wp = (uint32_t)align_up((size_t)need + 15, 16);
+      if (wp <= 256 && need <= 256 && (size_t)wp * need <= 48 * 1024) {
+        win_wp = wp;
+        win_h = (uint32_t)need;
+      }
+    }
+  }
+
+  // ---- arena layout --------------------------------------------------------------------------
+  const uint32_t map_pitch = (uint32_t)align_up(max_sx, 16);
+  const uint32_t map_rows = max_sy;
+  const size_t slot = (size_t)map_pitch * map_rows;
+  size_t off = 0;
+  const size_t o_scenes = off;
+  off = align_up(off + sizeof(SfwSceneDev) * n_scenes, kAlign);
+  const size_t o_pedA = off;
+  off = align_up(off + 16 * totP, kAlign);
+  const size_t o_pedB = off;
+  off = align_up(off + 16 * totP, kAlign);
+  const size_t o_pedC = off;
+  off = align_up(off + 16 * totP, kAlign);
+  const size_t o_obs = off;
+  off = align_up(off + 8 * totM, kAlign);
+  const size_t o_fp = off;
+  off = align_up(off + 16 * totF, kAlign);
+  const size_t o_lin = off;
+  off = align_up(off + 8 * (size_t)n_v, kAlign);
+  const size_t o_ang = off;
+  off = align_up(off + 8 * (size_t)n_w, kAlign);
+  const size_t o_maps = off;
+  off = align_up(off + slot * n_scenes, kAlign);
+  const size_t in_bytes = off;
+  int rc = arena_reserve(c, c->in, in_bytes);
+  if (rc != SFW_OK)
+    return rc;
+
+  // ---- pack ----------------------------------------------------------------------------------
+  uint8_t *h = c->in.host;
+  SfwSceneDev *hs = reinterpret_cast<SfwSceneDev *>(h + o_scenes);
+  float4 *hA = reinterpret_cast<float4 *>(h + o_pedA);
+  float4 *hB = reinterpret_cast<float4 *>(h + o_pedB);
+  float4 *hC = reinterpret_cast<float4 *>(h + o_pedC);
+  float2 *hO = reinterpret_cast<float2 *>(h + o_obs);
+  double2 *hF = reinterpret_cast<double2 *>(h + o_fp);
+  memcpy(h + o_lin, linvels, 8 * (size_t)n_v);
+  memcpy(h + o_ang, angvels, 8 * (size_t)n_w);
+  uint32_t pP = 0, pM = 0, pF = 0;
+  const double inv_sigma = 1.0 / sfm.force_sigma_obstacle;
+  for (uint32_t s = 0; s < n_scenes; ++s) {
+    const SfwScene &sc = scenes[s];
+    const SfwRobot &R = sc.robot;
+    SfwSceneDev &d = hs[s];
+    memset(&d, 0, sizeof(d));
+    d.rx = R.x;
+    d.ry = R.y;
+    d.rth = R.theta;
+    d.rvx = R.vx;
+    d.rvy = R.vy;
+    d.rvth = R.vtheta;
+    d.wpx = R.wpx;
+    d.wpy = R.wpy;
+    d.origin_x = sc.origin_x;
+    d.origin_y = sc.origin_y;
+    d.resolution = sc.resolution;
+    d.ax = (float)(R.agent_x - R.x);
+    d.ay = (float)(R.agent_y - R.y);
+    d.avx = (float)R.agent_vx;
+    d.avy = (float)R.agent_vy;
+    const double obs_norm = sc.n_obstacles ? sfm.force_factor_obstacle / (double)sc.n_obstacles : 0.0;
+    d.a_obs_scale = (float)(obs_norm * std::exp(R.agent_radius * inv_sigma));
+    d.size_x = sc.size_x;
+    d.size_y = sc.size_y;
+    d.win_x0 = wx0[s];
+    d.win_y0 = wy0[s];
+    d.n_peds = sc.n_peds;
+    d.n_obst = sc.n_obstacles;
+    d.n_fp = sc.n_footprint;
+    d.ped_off = pP;
+    d.obs_off = pM;
+    d.fp_off = pF;
+    d.map_off = slot * s;
+    for (uint32_t j = 0; j < sc.n_peds; ++j) {
+      const SfwPed &p = sc.peds[j];
+      hA[pP + j] = make_float4((float)(p.x - R.x), (float)(p.y - R.y), (float)p.vx, (float)p.vy);
+      hB[pP + j] = make_float4((float)(p.goal_x - R.x), (float)(p.goal_y - R.y),
+                               (float)(p.goal_radius * p.goal_radius), (float)p.desired_velocity);
+      hC[pP + j] = make_float4((float)(obs_norm * std::exp(p.radius * inv_sigma)),
+                               p.has_goal ? 1.0f : 0.0f,
+                               (float)(p.desired_velocity * p.desired_velocity), (float)p.group_id);
+    }
+    pP += sc.n_peds;
+    for (uint32_t k = 0; k < sc.n_obstacles; ++k)
+      hO[pM + k] = make_float2((float)(sc.obstacles_xy[2 * k] - R.x), (float)(sc.obstacles_xy[2 * k + 1] - R.y));
+    if (sc.n_obstacles & 1u)
+      hO[pM + sc.n_obstacles] = make_float2(0.f, 0.f);
+    pM += (uint32_t)align_up(sc.n_obstacles, 2);
+    for (uint32_t k = 0; k < sc.n_footprint; ++k)
+      hF[pF + k] = make_double2(sc.footprint_xy[2 * k], sc.footprint_xy[2 * k + 1]);
+    pF += sc.n_footprint;
+    uint8_t *dst = h + o_maps + slot * s;
+    if (sc.size_x == map_pitch) {
+      memcpy(dst, sc.costmap, (size_t)sc.size_x * sc.size_y);
+    } else {
+      for (uint32_t r = 0; r < sc.size_y; ++r)
+        memcpy(dst + (size_t)r * map_pitch, sc.costmap + (size_t)r * sc.size_x, sc.size_x);
+    }
+  }
+  CK(c, cudaMemcpyAsync(c->in.dev, c->in.host, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  c->in_bytes = in_bytes;
+  c->scene_host.assign(hs, hs + n_scenes);
+
+  // ---- outputs -------------------------------------------------------------------------------
+  const uint32_t samples = n_v * n_w;
+  rc = make_plan(c, n_scenes, samples, maxP, maxM, maxF, win_wp * win_h);
+  if (rc != SFW_OK)
+    return rc;
+  const uint32_t max_tiles = (samples + 31) / 32; // any slab / block size fits
+  size_t oo = 0;
+  c->off_best = oo;
+  oo = align_up(oo + sizeof(SfwBest) * n_scenes, kAlign);
+  c->off_costs = oo;
+  oo = align_up(oo + 4 * (size_t)samples * n_scenes, kAlign);
+  c->off_npts = oo;
+  oo = align_up(oo + 2 * (size_t)samples * n_scenes, kAlign);
+  c->off_bb = oo;
+  oo = align_up(oo + sizeof(SfwBlockBest) * (size_t)max_tiles * n_scenes, kAlign);
+  c->off_cnt = oo;
+  oo = align_up(oo + 4 * (size_t)n_scenes, kAlign);
+  const bool grew = oo > c->out.cap;
+  rc = arena_reserve(c, c->out, oo);
+  if (rc != SFW_OK)
+    return rc;
+  if (grew || c->out_scenes != n_scenes) // counters must start at 0; they self-reset afterwards
+    CK(c, cudaMemsetAsync(c->out.dev + c->off_cnt, 0, 4 * (size_t)n_scenes, c->stream));
+  c->out_scenes = n_scenes;
+  c->out_samples = samples;
+
+  // ---- batch descriptor ------------------------------------------------------------------------
+  SfwBatchDev &B = c->B;
+  memset(&B, 0, sizeof(B));
+  uint8_t *dv = c->in.dev;
+  B.scenes = reinterpret_cast<const SfwSceneDev *>(dv + o_scenes);
+  B.pedA = reinterpret_cast<const float4 *>(dv + o_pedA);
+  B.pedB = reinterpret_cast<const float4 *>(dv + o_pedB);
+  B.pedC = reinterpret_cast<const float4 *>(dv + o_pedC);
+  B.obst = reinterpret_cast<const float2 *>(dv + o_obs);
+  B.footprint = reinterpret_cast<const double2 *>(dv + o_fp);
+  B.maps = dv + o_maps;
+  B.linvels = reinterpret_cast<const double *>(dv + o_lin);
+  B.angvels = reinterpret_cast<const double *>(dv + o_ang);
+  B.costs = reinterpret_cast<float *>(c->out.dev + c->off_costs);
+  B.npts = reinterpret_cast<uint16_t *>(c->out.dev + c->off_npts);
+  B.best = reinterpret_cast<SfwBest *>(c->out.dev + c->off_best);
+  B.blockbest = reinterpret_cast<SfwBlockBest *>(c->out.dev + c->off_bb);
+  B.counters = reinterpret_cast<unsigned int *>(c->out.dev + c->off_cnt);
+  B.map_pitch = map_pitch;
+  B.map_rows = map_rows;
+  B.n_scenes = n_scenes;
+  B.n_v = n_v;
+  B.n_w = n_w;
+  B.row_begin = 0;
+  B.row_end = n_v;
+  B.tiles_per_scene = c->plan.tiles;
+  B.win_wp = win_wp;
+  B.win_h = win_h;
+  B.num_steps = num_steps;
+  B.dt = dt;
+  B.max_vel_x = params->max_vel_x;
+  B.acc_x = params->max_trans_acc;
+  B.acc_th = params->max_rot_acc;
+  B.w_vel = params->vel_weight;
+  B.w_dist = params->distance_weight;
+  B.w_ang = params->angle_weight;
+  B.w_map = params->costmap_weight;
+  B.w_soc = params->social_weight;
+  B.rr2 = params->robot_radius * params->robot_radius; // float product (sfw_planner.cpp:617)
+  const double log2e = 1.4426950408889634;
+  B.lambda = (float)sfm.lambda;
+  B.gamma = (float)sfm.gamma;
+  B.c_d = (float)(log2e / sfm.gamma);
+  B.c_np = (float)(sfm.n_prime * sfm.n_prime * log2e);
+  B.c_n = (float)(sfm.n * sfm.n * log2e);
+  B.k_soc = (float)sfm.force_factor_social;
+  B.kd_tau = (float)(sfm.force_factor_desired / sfm.relaxation_time);
+  B.inv_tau = (float)(1.0 / sfm.relaxation_time);
+  B.c_obs = (float)(log2e * inv_sigma);
+  B.dtf = (float)dt;
+  if (win_wp) {
+    rc = make_tensor_map(c, B.maps, map_pitch, map_rows, n_scenes, win_wp, win_h);
+    if (rc != SFW_OK)
+      return rc;
+  }
+
+  // SURVEY.md 8(d) algorithmic bytes
+  uint64_t ab = 0;
+  for (uint32_t s = 0; s < n_scenes; ++s) {
+    const SfwScene &sc = scenes[s];
+    ab += (uint64_t)sc.size_x * sc.size_y + 32ull * sc.n_peds + 8ull * sc.n_obstacles +
+          16ull * sc.n_footprint + 128ull + 4ull * (n_v + n_w) + 4ull * samples + 16ull;
+  }
+  c->algo_bytes = ab;
+  c->slab_begin = 0;
+  c->slab_end = 0xffffffffu;
+  c->staged = true;
+  return SFW_OK;
+}
+
+int sfw_set_row_slab(sfw_ctx *c, uint32_t row_begin, uint32_t row_end) {
+  if (!c)
+    return SFW_ERR_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->staged)
+    return fail(c, SFW_ERR_STATE, "sfw_set_row_slab before sfw_upload");
+  if (row_end > c->B.n_v)
+    row_end = c->B.n_v;
+  if (row_begin > row_end)
+    return fail(c, SFW_ERR_ARG, "row_begin > row_end");
+  c->slab_begin = row_begin;
+  c->slab_end = row_end;
+  return SFW_OK;
+}
+
+int sfw_run(sfw_ctx *c) {
+  if (!c)
+    return SFW_ERR_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->staged)
+    return fail(c, SFW_ERR_STATE, "sfw_run before sfw_upload");
+  CK(c, cudaSetDevice(c->device));
+  SfwBatchDev &B = c->B;
+  const uint32_t rb = std::min(c->slab_begin, B.n_v), re = std::min(c->slab_end, B.n_v);
+  if (rb != B.row_begin || re != B.row_end) {
+    // rows outside the slab keep SFW_COST_SKIPPED
+    B.row_begin = rb;
+    B.row_end = re;
+    const uint32_t samples = (re - rb) * B.n_w;
+    Plan saved = c->plan;
+    c->plan.valid = false;
+    int rc = make_plan(c, B.n_scenes, std::max(samples, 1u), saved.maxP, saved.maxM, saved.maxF,
+                       saved.win_bytes);
+    if (rc != SFW_OK)
+      return rc;
+    B.tiles_per_scene = c->plan.tiles;
+    // fill the whole cost vector with SKIPPED once; the kernel overwrites the slab
+    const size_t n = (size_t)B.n_scenes * B.n_v * B.n_w;
+    {
+      // cudaMemsetAsync only sets bytes; -2.0f = 0xC0000000 needs a 32-bit fill
+      CUresult (*fill32)(CUdeviceptr, unsigned int, size_t, CUstream) = nullptr;
+      void *p = nullptr;
+      cudaDriverEntryPointQueryResult qr;
+      if (cudaGetDriverEntryPoint("cuMemsetD32Async", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+          qr == cudaDriverEntryPointSuccess) {
+        fill32 = (CUresult(*)(CUdeviceptr, unsigned int, size_t, CUstream))p;
+        if (fill32((CUdeviceptr)(uintptr_t)B.costs, 0xC0000000u, n, (CUstream)c->stream) != CUDA_SUCCESS)
+          return fail(c, SFW_ERR_CUDA, "cuMemsetD32Async failed");
+      } else {
+        return fail(c, SFW_ERR_CUDA, "cuMemsetD32Async entry point unavailable");
+      }
+    }
+    CK(c, cudaMemsetAsync(B.npts, 0, n * 2, c->stream));
+  }
+  if (re > rb) {
+    CK(c, sfw_launch_small(B, c->tmap, c->plan.T, c->plan.smem, c->stream));
+    c->launches += 1;
+    c->last_kernel = "sfw_score_small";
+  } else {
+    // empty slab: nothing to score, every scene reports "no valid trajectory"
+    CK(c, cudaMemsetAsync(B.best, 0, sizeof(SfwBest) * B.n_scenes, c->stream));
+  }
+  c->ran = true;
+  return SFW_OK;
+}
+
+int sfw_sync(sfw_ctx *c) {
+  if (!c)
+    return SFW_ERR_ARG;
+  CK(c, cudaStreamSynchronize(c->stream));
+  return SFW_OK;
+}
+
+int sfw_download(sfw_ctx *c, float *costs_out, SfwBest *best_out) {
+  if (!c)
+    return SFW_ERR_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->ran)
+    return fail(c, SFW_ERR_STATE, "sfw_download before sfw_run");
+  CK(c, cudaSetDevice(c->device));
+  const size_t nb = sizeof(SfwBest) * c->B.n_scenes;
+  const size_t nc = 4 * (size_t)c->out_samples * c->B.n_scenes;
+  if (best_out)
+    CK(c, cudaMemcpyAsync(c->out.host + c->off_best, c->out.dev + c->off_best, nb,
+                          cudaMemcpyDeviceToHost, c->stream));
+  if (costs_out)
+    CK(c, cudaMemcpyAsync(c->out.host + c->off_costs, c->out.dev + c->off_costs, nc,
+                          cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  if (best_out)
+    memcpy(best_out, c->out.host + c->off_best, nb);
+  if (costs_out)
+    memcpy(costs_out, c->out.host + c->off_costs, nc);
+  return SFW_OK;
+}
+
+int sfw_score_batch(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm,
+                    const SfwScene *scenes, uint32_t n_scenes, const double *linvels, uint32_t n_v,
+                    const double *angvels, uint32_t n_w, float *costs_out, SfwBest *best_out) {
+  int rc = sfw_upload(c, params, sfm, scenes, n_scenes, linvels, n_v, angvels, n_w);
+  if (rc != SFW_OK)
+    return rc;
+  rc = sfw_run(c);
+  if (rc != SFW_OK)
+    return rc;
+  return sfw_download(c, costs_out, best_out);
+}
+
+int sfw_score(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm, const SfwScene *scene,
+              const double *linvels, uint32_t n_v, const double *angvels, uint32_t n_w,
+              float *costs_out, SfwBest *best_out) {
+  return sfw_score_batch(c, params, sfm, scene, 1, linvels, n_v, angvels, n_w, costs_out, best_out);
+}
+
+int sfw_trajectory_points(sfw_ctx *c, uint32_t scene, uint32_t sample_index, double *xyz_out,
+                          uint32_t max_points, uint32_t *n_points) {
+  if (!c)
+    return SFW_ERR_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->ran)
+    return fail(c, SFW_ERR_STATE, "sfw_trajectory_points before sfw_run");
+  if (scene >= c->B.n_scenes || sample_index >= c->out_samples || !n_points)
+    return fail(c, SFW_ERR_ARG, "sfw_trajectory_points: index out of range");
+  CK(c, cudaSetDevice(c->device));
+  uint16_t np16 = 0;
+  CK(c, cudaMemcpyAsync(&np16, c->B.npts + (size_t)scene * c->out_samples + sample_index, 2,
+                        cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  *n_points = np16;
+  const uint32_t n = std::min<uint32_t>(np16, max_points);
+  if (!n || !xyz_out)
+    return SFW_OK;
+  if (n > c->points_cap) {
+    if (c->d_points)
+      cudaFree(c->d_points);
+    if (c->h_points)
+      cudaFreeHost(c->h_points);
+    c->d_points = nullptr;
+    c->h_points = nullptr;
+    c->points_cap = 0;
+    CK(c, cudaMalloc((void **)&c->d_points, 24 * (size_t)n));
+    CK(c, cudaMallocHost((void **)&c->h_points, 24 * (size_t)n));
+    c->points_cap = n;
+  }
+  CK(c, sfw_launch_points(c->B, scene, sample_index, n, c->d_points, c->stream));
+  c->launches += 1;
+  CK(c, cudaMemcpyAsync(c->h_points, c->d_points, 24 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  memcpy(xyz_out, c->h_points, 24 * (size_t)n);
+  return SFW_OK;
+}
+
+void *sfw_stream(sfw_ctx *c) { return c ? (void *)c->stream : nullptr; }
+const float *sfw_device_costs(sfw_ctx *c) { return (c && c->staged) ? c->B.costs : nullptr; }
+const void *sfw_device_best(sfw_ctx *c) { return (c && c->staged) ? (const void *)c->B.best : nullptr; }
+uint64_t sfw_kernel_launches(const sfw_ctx *c) { return c ? c->launches : 0; }
+uint64_t sfw_algorithmic_bytes(const sfw_ctx *c) { return c ? c->algo_bytes : 0; }
+const char *sfw_last_kernel(const sfw_ctx *c) { return c ? c->last_kernel : "none"; }
+
+} // extern "C"

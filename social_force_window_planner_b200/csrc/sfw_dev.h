@@ -1,0 +1,84 @@
+// sfw_dev.h — device-side data layout shared by the host packer (sfw_abi.cu) and the kernels
+// (sfw_kernels.cu).  Everything here is OUR layout in HBM (DESIGN.md "Data layout"); the caller
+// facing types live in include/sfw_b200.h.
+//
+// Frame convention: pedestrians, obstacle points and the robot's SFM position are stored in FP32
+// relative to the rollout start pose (robot.x, robot.y) of their scene, computed in FP64 on the
+// host before narrowing.  The social-force model only ever uses position differences, so the
+// translation is exact in the model and keeps FP32 resolution (~1e-7 m) independent of where the
+// odom frame's origin is.  The robot rollout itself and every costmap cell index stay in FP64
+// world coordinates so that cell choice is bit-identical to the reference.
+#ifndef SFW_DEV_H
+#define SFW_DEV_H
+
+#include <stdint.h>
+
+#include "../../include/sfw_b200.h"
+
+#define SFW_MAX_PEDS_SMALL 64 /* thread-per-trajectory kernel: goal flags live in one 64-bit mask */
+#define SFW_MAX_FOOTPRINT 64
+#define SFW_MAX_BLOCK_SMALL 512 /* launch bound of the thread-per-trajectory kernel (128 regs/thread) */
+
+struct SfwSceneDev {
+  // robot rollout start (FP64 world frame) — SfwRobot
+  double rx, ry, rth, rvx, rvy, rvth;
+  double wpx, wpy;
+  // costmap geometry
+  double origin_x, origin_y, resolution;
+  // agents[0] as the sensor interface saw it, scene frame FP32
+  float ax, ay, avx, avy;
+  float a_obs_scale; // (k_obs / M) * exp(agent_radius / sigma)
+  uint32_t size_x, size_y;
+  int32_t win_x0, win_y0; // first cell of the staged window (may be negative / beyond the map)
+  uint32_t n_peds, n_obst, n_fp;
+  uint32_t ped_off, obs_off, fp_off; // element offsets into the packed arrays
+  uint32_t pad0;
+  uint64_t map_off; // byte offset of this scene's costmap slot
+};
+
+struct SfwBlockBest {
+  float cost; // < 0 => no valid trajectory in the tile
+  uint32_t index;
+};
+
+struct SfwBatchDev {
+  const SfwSceneDev *scenes;
+  const float4 *pedA; // x, y, vx, vy            (scene frame)
+  const float4 *pedB; // goal_x, goal_y, goal_r^2, desired_velocity
+  const float4 *pedC; // obs_scale, has_goal (0/1), desired_velocity^2, group id (as float)
+  const float2 *obst; // obstacle points (scene frame)
+  const double2 *footprint;
+  const uint8_t *maps; // costmap slots: map_rows rows of map_pitch bytes each
+  const double *linvels;
+  const double *angvels;
+  float *costs;        // [n_scenes][n_v*n_w]
+  uint16_t *npts;      // [n_scenes][n_v*n_w] trajectory points recorded before the rollout stopped
+  SfwBest *best;       // [n_scenes]
+  SfwBlockBest *blockbest; // [n_scenes][tiles_per_scene]
+  unsigned int *counters;  // [n_scenes] tiles finished (self-resetting)
+  uint32_t map_pitch, map_rows;
+  uint32_t n_scenes, n_v, n_w;
+  uint32_t row_begin, row_end; // linvel rows scored by this launch
+  uint32_t tiles_per_scene;
+  uint32_t win_wp, win_h; // staged window box (padded width, rows); 0 => read the map from global
+  int32_t num_steps;
+  uint32_t pad0;
+  double dt;
+  // ControllerParams on the path
+  double max_vel_x, acc_x, acc_th;
+  double w_vel, w_dist, w_ang, w_map, w_soc;
+  float rr2; // robot_radius * robot_radius evaluated in float (reference sfw_planner.cpp:617)
+  // lightsfm constants folded for the FP32 force evaluator
+  float lambda;     // lambda
+  float gamma;      // gamma
+  float c_d;        // log2(e) / gamma            : -d/B * log2e = -d * rL * c_d
+  float c_np;       // n'^2 * log2(e)
+  float c_n;        // n^2 * log2(e)
+  float k_soc;      // forceFactorSocial
+  float kd_tau;     // forceFactorDesired / relaxationTime
+  float inv_tau;    // 1 / relaxationTime
+  float c_obs;      // log2(e) / sigma
+  float dtf;        // (float)dt
+};
+
+#endif

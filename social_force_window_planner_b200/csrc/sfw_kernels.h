@@ -1,0 +1,17 @@
+// sfw_kernels.h — launch wrappers of the scorer kernels (sfw_kernels.cu), called by sfw_abi.cu.
+#ifndef SFW_KERNELS_H
+#define SFW_KERNELS_H
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "sfw_dev.h"
+
+// dynamic shared memory of sfw_score_small for a block of T threads
+size_t sfw_small_smem_bytes(uint32_t win_bytes, uint32_t P, uint32_t M, uint32_t F, uint32_t T);
+cudaError_t sfw_small_max_dynamic_smem(size_t *bytes);
+cudaError_t sfw_small_occupancy(uint32_t T, size_t smem_bytes, int *blocks_per_sm);
+cudaError_t sfw_launch_small(const SfwBatchDev &B, const CUtensorMap &tmap, uint32_t T,
+                             size_t smem_bytes, cudaStream_t stream);
+cudaError_t sfw_launch_points(const SfwBatchDev &B, uint32_t scene, uint32_t idx, uint32_t n_points,
+                              double *out_xyz, cudaStream_t stream);
+#endif

@@ -1,0 +1,123 @@
+"""`Scorer`: thin object wrapper over one ``sfw_ctx`` of the C ABI.
+
+Every method is a direct call into ``libsfw_b200.so``; results come from the CUDA kernels only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._abi import BEST_DTYPE, SceneArray, SfwBest, SfwParams, SfwSfmParams
+
+_dp = C.POINTER(C.c_double)
+_fp = C.POINTER(C.c_float)
+
+
+class SfwError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"sfw error {code}: {msg}")
+        self.code = code
+
+
+class Scorer:
+    """One scoring context (device buffers + stream) on one GPU."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._lib = _lib.lib()
+        self._ctx = C.c_void_p()
+        rc = self._lib.sfw_create(C.byref(self._ctx), device, C.c_void_p(stream) if stream else None,
+                                  None)
+        if rc != 0:
+            msg = self._lib.sfw_last_error(None).decode()
+            self._ctx = C.c_void_p()
+            raise SfwError(rc, msg)
+        self._keep = None
+        self.n_scenes = 0
+        self.n_samples = 0
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.sfw_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise SfwError(rc, self._lib.sfw_last_error(self._ctx).decode())
+
+    # -- split form -------------------------------------------------------------------------
+    def upload(self, params: SfwParams, scenes, linvels, angvels, sfm: SfwSfmParams | None = None):
+        sa = scenes if isinstance(scenes, SceneArray) else SceneArray(scenes)
+        lin = np.ascontiguousarray(linvels, dtype=np.float64)
+        ang = np.ascontiguousarray(angvels, dtype=np.float64)
+        self._keep = (sa, lin, ang)
+        self._check(self._lib.sfw_upload(self._ctx, C.byref(params), C.byref(sfm) if sfm else None,
+                                         sa.ptr(0), len(sa), lin.ctypes.data_as(_dp), len(lin),
+                                         ang.ctypes.data_as(_dp), len(ang)))
+        self.n_scenes = len(sa)
+        self.n_samples = len(lin) * len(ang)
+
+    def set_row_slab(self, row_begin: int, row_end: int):
+        self._check(self._lib.sfw_set_row_slab(self._ctx, row_begin, row_end))
+
+    def run(self):
+        self._check(self._lib.sfw_run(self._ctx))
+
+    def sync(self):
+        self._check(self._lib.sfw_sync(self._ctx))
+
+    def download(self, want_costs: bool = True):
+        best = np.zeros(self.n_scenes, dtype=BEST_DTYPE)
+        costs = np.empty((self.n_scenes, self.n_samples), dtype=np.float32) if want_costs else None
+        self._check(self._lib.sfw_download(
+            self._ctx, costs.ctypes.data_as(_fp) if want_costs else None,
+            best.ctypes.data_as(C.POINTER(SfwBest))))
+        return costs, best
+
+    # -- one-call form ------------------------------------------------------------------------
+    def score(self, params, scenes, linvels, angvels, sfm=None, want_costs=True):
+        """``sfw_score_batch``: returns (costs[n_scenes, n_v*n_w] float32 or None, best[n_scenes])."""
+        sa = scenes if isinstance(scenes, SceneArray) else SceneArray(scenes)
+        lin = np.ascontiguousarray(linvels, dtype=np.float64)
+        ang = np.ascontiguousarray(angvels, dtype=np.float64)
+        self._keep = (sa, lin, ang)
+        self.n_scenes = len(sa)
+        self.n_samples = len(lin) * len(ang)
+        best = np.zeros(self.n_scenes, dtype=BEST_DTYPE)
+        costs = np.empty((self.n_scenes, self.n_samples), dtype=np.float32) if want_costs else None
+        self._check(self._lib.sfw_score_batch(
+            self._ctx, C.byref(params), C.byref(sfm) if sfm else None, sa.ptr(0), len(sa),
+            lin.ctypes.data_as(_dp), len(lin), ang.ctypes.data_as(_dp), len(ang),
+            costs.ctypes.data_as(_fp) if want_costs else None, best.ctypes.data_as(C.POINTER(SfwBest))))
+        return costs, best
+
+    def trajectory_points(self, scene: int, sample_index: int, max_points: int = 65535):
+        n = C.c_uint32(0)
+        buf = np.zeros((max_points, 3), dtype=np.float64)
+        self._check(self._lib.sfw_trajectory_points(self._ctx, scene, sample_index,
+                                                    buf.ctypes.data_as(_dp), max_points, C.byref(n)))
+        return buf[: min(n.value, max_points)].copy(), n.value
+
+    # -- introspection --------------------------------------------------------------------------
+    @property
+    def stream(self) -> int:
+        return self._lib.sfw_stream(self._ctx) or 0
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._lib.sfw_kernel_launches(self._ctx))
+
+    @property
+    def algorithmic_bytes(self) -> int:
+        return int(self._lib.sfw_algorithmic_bytes(self._ctx))
+
+    @property
+    def last_kernel(self) -> str:
+        return self._lib.sfw_last_kernel(self._ctx).decode()
