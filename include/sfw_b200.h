@@ -206,6 +206,10 @@ const void *sfw_device_best(sfw_ctx *ctx);      /* device SfwBest[n_scenes] of t
 uint64_t sfw_kernel_launches(const sfw_ctx *ctx); /* kernels launched by this context so far */
 /* algorithmic bytes of the staged batch (SURVEY.md section 8d formula) */
 uint64_t sfw_algorithmic_bytes(const sfw_ctx *ctx);
+/* bytes the last sfw_upload copied host->device, and bytes sfw_download copies back when both the
+ * cost vector and the winners are requested (bench.py's e2e accounting) */
+uint64_t sfw_h2d_bytes(const sfw_ctx *ctx);
+uint64_t sfw_d2h_bytes(const sfw_ctx *ctx);
 /* name of the kernel variant the last sfw_run dispatched to (for logs/profiles) */
 const char *sfw_last_kernel(const sfw_ctx *ctx);
 

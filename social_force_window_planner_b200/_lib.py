@@ -19,7 +19,7 @@ EXPORTS = [
     "sfw_default_sfm_params", "sfw_score", "sfw_score_batch", "sfw_upload", "sfw_run",
     "sfw_download", "sfw_sync", "sfw_set_row_slab", "sfw_trajectory_points", "sfw_stream",
     "sfw_device_costs", "sfw_device_best", "sfw_kernel_launches", "sfw_algorithmic_bytes",
-    "sfw_last_kernel",
+    "sfw_last_kernel", "sfw_h2d_bytes", "sfw_d2h_bytes",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -73,6 +73,9 @@ def load() -> C.CDLL:
     lib.sfw_kernel_launches.argtypes = [_ctx]
     lib.sfw_algorithmic_bytes.restype = C.c_uint64
     lib.sfw_algorithmic_bytes.argtypes = [_ctx]
+    for f in (lib.sfw_h2d_bytes, lib.sfw_d2h_bytes):
+        f.restype = C.c_uint64
+        f.argtypes = [_ctx]
     lib.sfw_last_kernel.restype = C.c_char_p
     lib.sfw_last_kernel.argtypes = [_ctx]
     return lib

@@ -789,6 +789,10 @@ const float *sfw_device_costs(sfw_ctx *c) { return (c && c->staged) ? c->B.costs
 const void *sfw_device_best(sfw_ctx *c) { return (c && c->staged) ? (const void *)c->B.best : nullptr; }
 uint64_t sfw_kernel_launches(const sfw_ctx *c) { return c ? c->launches : 0; }
 uint64_t sfw_algorithmic_bytes(const sfw_ctx *c) { return c ? c->algo_bytes : 0; }
+uint64_t sfw_h2d_bytes(const sfw_ctx *c) { return c ? c->in_bytes : 0; }
+uint64_t sfw_d2h_bytes(const sfw_ctx *c) {
+  return (c && c->staged) ? (sizeof(SfwBest) + 4ull * c->out_samples) * c->B.n_scenes : 0;
+}
 const char *sfw_last_kernel(const sfw_ctx *c) { return c ? c->last_kernel : "none"; }
 
 } // extern "C"

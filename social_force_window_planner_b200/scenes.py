@@ -223,9 +223,21 @@ def _make_obstacles(cm: np.ndarray, res: float, ox: float, oy: float, m: int) ->
     return np.array(pts, dtype=np.float64)
 
 
+def _stamp_box(cm, res, ox, oy, x0, x1, y0, y1, ring=0.3):
+    """Lethal box [x0,x1]x[y0,y1] with an exponential inflation ring, max-merged into ``cm``."""
+    h, w = cm.shape
+    xs = ox + (np.arange(w) + 0.5) * res
+    ys = oy + (np.arange(h) + 0.5) * res
+    dx = np.maximum(np.maximum(x0 - xs[None, :], xs[None, :] - x1), 0.0)
+    dy = np.maximum(np.maximum(y0 - ys[:, None], ys[:, None] - y1), 0.0)
+    d = np.hypot(dx, dy)
+    cost = np.where(d <= 0.0, 254, np.where(d <= ring, np.floor(252.0 * np.exp(-6.0 * d)), 0))
+    np.maximum(cm, cost.astype(np.uint8), out=cm)
+
+
 def make_scene(workload: Workload, scene_index: int = 0, *, n_peds: int | None = None,
                n_obstacles: int | None = None, footprint: np.ndarray | None = None,
-               robot_xy=(0.0, 0.0), robot_theta: float = 0.0) -> Scene:
+               robot_xy=(0.0, 0.0), robot_theta: float = 0.0, hazards: bool = False) -> Scene:
     """Build scene ``scene_index`` of a workload (seed = 1000 + scene_index).
 
     ``robot_xy``/``robot_theta`` translate/rotate nothing but the robot start pose and the whole
@@ -239,6 +251,16 @@ def make_scene(workload: Workload, scene_index: int = 0, *, n_peds: int | None =
     p = workload.n_peds if n_peds is None else n_peds
     r_max = workload.ped_r_max if workload.ped_r_max is not None else min(4.0, 0.45 * w * res)
     peds = _make_peds(rng, p, r_max, workload.ped_sep)
+    if hazards:
+        # a lethal box the faster straight rollouts drive into, an unknown (255) patch on the right
+        # and (when there are pedestrians) one that walks across the robot's path: exercises every
+        # rejection branch of scoreTrajectory (sfw_planner.cpp:545-573, :613-627)
+        _stamp_box(cm, res, ox, oy, 0.62, 0.85, 0.05, 0.40)
+        cm[int((-0.62 - oy) / res):int((-0.50 - oy) / res), int((0.30 - ox) / res):int((0.45 - ox) / res)] = 255
+        if p > 0:
+            q = peds[0]
+            q["x"], q["y"], q["vx"], q["vy"] = 0.45, -0.75, 0.0, 0.8
+            q["goal_x"], q["goal_y"] = 0.45, -0.75 + 2.0 * 0.8
     m = workload.n_obstacles if n_obstacles is None else n_obstacles
     obs = _make_obstacles(cm, res, ox, oy, m)
     fp = circle_footprint() if footprint is None else np.asarray(footprint, dtype=np.float64)

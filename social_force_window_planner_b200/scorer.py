@@ -119,5 +119,13 @@ class Scorer:
         return int(self._lib.sfw_algorithmic_bytes(self._ctx))
 
     @property
+    def h2d_bytes(self) -> int:
+        return int(self._lib.sfw_h2d_bytes(self._ctx))
+
+    @property
+    def d2h_bytes(self) -> int:
+        return int(self._lib.sfw_d2h_bytes(self._ctx))
+
+    @property
     def last_kernel(self) -> str:
         return self._lib.sfw_last_kernel(self._ctx).decode()
