@@ -473,6 +473,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   memcpy(h + o_ang, angvels, 8 * (size_t)n_w);
   uint32_t pP = 0, pM = 0, pF = 0;
   const double inv_sigma = 1.0 / sfm.force_sigma_obstacle;
+  const double c_obs_d = (double)(float)(1.4426950408889634 * inv_sigma); // the float the kernel multiplies by
   for (uint32_t s = 0; s < n_scenes; ++s) {
     const SfwScene &sc = scenes[s];
     const SfwRobot &R = sc.robot;
@@ -516,8 +517,10 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
                                (float)(p.desired_velocity * p.desired_velocity), (float)p.group_id);
     }
     pP += sc.n_peds;
+    // obstacle points: scene frame, pre-multiplied by log2(e)/sigma (see obstacle_sum)
     for (uint32_t k = 0; k < sc.n_obstacles; ++k)
-      hO[pM + k] = make_float2((float)(sc.obstacles_xy[2 * k] - R.x), (float)(sc.obstacles_xy[2 * k + 1] - R.y));
+      hO[pM + k] = make_float2((float)((sc.obstacles_xy[2 * k] - R.x) * c_obs_d),
+                               (float)((sc.obstacles_xy[2 * k + 1] - R.y) * c_obs_d));
     if (sc.n_obstacles & 1u)
       hO[pM + sc.n_obstacles] = make_float2(0.f, 0.f);
     pM += (uint32_t)align_up(sc.n_obstacles, 2);
@@ -553,12 +556,12 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   oo = align_up(oo + sizeof(SfwBlockBest) * (size_t)max_tiles * n_scenes, kAlign);
   c->off_cnt = oo;
   oo = align_up(oo + 4 * (size_t)n_scenes, kAlign);
-  const bool grew = oo > c->out.cap;
   rc = arena_reserve(c, c->out, oo);
   if (rc != SFW_OK)
     return rc;
-  if (grew || c->out_scenes != n_scenes) // counters must start at 0; they self-reset afterwards
-    CK(c, cudaMemsetAsync(c->out.dev + c->off_cnt, 0, 4 * (size_t)n_scenes, c->stream));
+  // The tile counters must start at 0 (they self-reset after every launch).  Their offset moves with
+  // the sample count, so clear them on every upload: 4 bytes per scene on the same stream.
+  CK(c, cudaMemsetAsync(c->out.dev + c->off_cnt, 0, 4 * (size_t)n_scenes, c->stream));
   c->out_scenes = n_scenes;
   c->out_samples = samples;
 

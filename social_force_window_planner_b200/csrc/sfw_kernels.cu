@@ -121,7 +121,7 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, 
 // scaled by forceFactorSocial.  e_ang is the magnitude of the angular term, used for |F|.
 // ------------------------------------------------------------------------------------------------
 struct SfmConst {
-  float lambda, c_d, gamma, c_np, c_n, k_soc;
+  float lambda, c_d, g2, c_np, c_n, k_soc; // g2 = gamma^2
 };
 
 // atan(t) for t in [0,1]: odd minimax polynomial, |err| < 1e-7 in FP32 (fit in DESIGN.md)
@@ -139,56 +139,63 @@ __device__ __forceinline__ float atan01(float t) {
   return p * t;
 }
 
+// WITH_MAG: also return |F| (only the robot-pedestrian pairs need it, for the social work).
+template <bool WITH_MAG>
 __device__ __forceinline__ void pair_force(const SfmConst &K, float ax, float ay, float avx,
                                            float avy, float bx, float by, float bvx, float bvy,
                                            float &fx, float &fy, float &fmag) {
   const float dx = bx - ax, dy = by - ay;
-  float d2 = fmaf(dx, dx, dy * dy);
-  d2 = fmaxf(d2, 1e-30f);
+  const float d2 = fmaf(dx, dx, fmaf(dy, dy, 1e-30f));    // +eps: coincident agents give 0, not NaN
   const float rd = rsqrt_approx(d2);
-  const float d = d2 * rd;
   const float ex = dx * rd, ey = dy * rd;                 // diffDirection
   const float ix = fmaf(K.lambda, avx - bvx, ex);         // interactionVector
   const float iy = fmaf(K.lambda, avy - bvy, ey);
-  float L2 = fmaf(ix, ix, iy * iy);
-  L2 = fmaxf(L2, 1e-30f);
-  const float rL = rsqrt_approx(L2);
-  const float L = L2 * rL;                                // interactionLength
-  // theta = angle from interactionDirection to diffDirection = atan2(i x e, i . e)
-  const float sn = fmaf(ix, ey, -(iy * ex));
+  const float L2 = fmaf(ix, ix, fmaf(iy, iy, 1e-30f));
+  const float rL = rsqrt_approx(L2);                      // 1 / interactionLength
+  // theta = angle from interactionDirection to diffDirection = atan2(i x e, i . e).  The cross
+  // product is a difference of two ROUNDED products (no FMA) so that equal velocities (i == e
+  // bit for bit) give exactly theta = 0 and no angular term, as lightsfm's Angle::sign() does.
+  const float sn = __fsub_rn(__fmul_rn(ix, ey), __fmul_rn(iy, ex));
   const float cs = fmaf(ix, ex, iy * ey);
   const float asn = fabsf(sn), acs = fabsf(cs);
   const float mx = fmaxf(asn, acs), mn = fminf(asn, acs);
   float th = atan01(mn * rcp_approx(fmaxf(mx, 1e-30f)));
   th = (asn > acs) ? (1.5707963267948966f - th) : th;
   th = (cs < 0.0f) ? (3.14159265358979f - th) : th;       // |theta| in [0, pi]
-  const float Bt = K.gamma * L * th;                      // B * theta
-  const float q = Bt * Bt;
-  const float t = -(d * rL) * K.c_d;                      // -|diff| / B  (in log2 units)
+  const float q = (K.g2 * L2) * (th * th);                // (B theta)^2, B = gamma * interactionLength
+  const float t = -((d2 * rd) * rL) * K.c_d;              // -|diff| / B  (in log2 units)
   const float e_vel = ex2_approx(fmaf(-K.c_np, q, t));    // exp(-d/B - (n' B theta)^2)
   const float e_ang = ex2_approx(fmaf(-K.c_n, q, t));     // exp(-d/B - (n  B theta)^2)
-  // sign(theta): 0 only for theta == 0 exactly; theta == pi counts as positive (lightsfm Angle)
-  float sg = (sn > 0.0f) ? 1.0f : ((sn < 0.0f) ? -1.0f : ((cs < 0.0f) ? 1.0f : 0.0f));
-  const float fv = -e_vel * rL * K.k_soc;                 // along interactionVector (unnormalised)
-  const float fa = -sg * e_ang * rL * K.k_soc;            // along its left normal
-  fx = fmaf(fv, ix, -(fa * iy));
-  fy = fmaf(fv, iy, fa * ix);
-  const float ea = fabsf(sg) * e_ang;
-  fmag = K.k_soc * sqrt_approx(fmaf(e_vel, e_vel, ea * ea));
+  const float rLk = rL * K.k_soc;
+  const float fv = e_vel * rLk;                           // -(force along interactionVector)
+  // forceAngle = -sign(theta) * e_ang along the left normal.  sign(theta) is 0 only for theta == 0
+  // exactly; theta == pi counts as positive (lightsfm Angle wraps to (-pi, pi]).
+  float fa = __uint_as_float(__float_as_uint(e_ang * rLk) | (__float_as_uint(sn) & 0x80000000u));
+  if (sn == 0.0f)
+    fa = (cs < 0.0f) ? fabsf(fa) : 0.0f;                  // here fa = +sign(theta) * magnitude
+  // F = -fv * i - fa * leftNormal(i), leftNormal(i) = (-iy, ix)
+  fx = fmaf(fa, iy, -(fv * ix));
+  fy = -fmaf(fa, ix, fv * iy);
+  if (WITH_MAG) {
+    const float ea = (sn == 0.0f && cs >= 0.0f) ? 0.0f : e_ang;
+    fmag = K.k_soc * sqrt_approx(fmaf(e_vel, e_vel, ea * ea));
+  }
 }
 
-// lightsfm obstacle force sum (unscaled): sum_o exp(-|p-o|/sigma) (p-o)/|p-o|
+// lightsfm obstacle force sum (unscaled): sum_o exp(-|p-o|/sigma) (p-o)/|p-o|.  Obstacle points are
+// stored pre-multiplied by c_obs = log2(e)/sigma, and so is the query point: then |p'-o'| is the
+// exponent in log2 units and the unit vector is unchanged.
 __device__ __forceinline__ void obstacle_sum(const float2 *__restrict__ obs, int M, float c_obs,
                                              float px, float py, float &sx, float &sy) {
   float ax = 0.f, ay = 0.f;
+  const float qx = px * c_obs, qy = py * c_obs;
 #pragma unroll 4
   for (int o = 0; o < M; ++o) {
     const float2 p = obs[o];
-    const float dx = px - p.x, dy = py - p.y;
-    float d2 = fmaf(dx, dx, dy * dy);
-    d2 = fmaxf(d2, 1e-30f);
+    const float dx = qx - p.x, dy = qy - p.y;
+    const float d2 = fmaf(dx, dx, fmaf(dy, dy, 1e-30f));
     const float rd = rsqrt_approx(d2);
-    const float e = ex2_approx(-(d2 * rd) * c_obs) * rd;
+    const float e = ex2_approx(-(d2 * rd)) * rd;
     ax = fmaf(e, dx, ax);
     ay = fmaf(e, dy, ay);
   }
@@ -424,7 +431,7 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   mv.wwp = win_bytes ? B.win_wp : 0u;
   mv.wh = win_bytes ? B.win_h : 0u;
 
-  const SfmConst K = {B.lambda, B.c_d, B.gamma, B.c_np, B.c_n, B.k_soc};
+  const SfmConst K = {B.lambda, B.c_d, B.gamma * B.gamma, B.c_np, B.c_n, B.k_soc};
 
   // ---- which trajectory is mine ----------------------------------------------------------------
   const uint32_t n_w = B.n_w;
@@ -469,14 +476,20 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   for (int i = 0; i < S; ++i) {
     if (!__any_sync(0xffffffffu, alive))
       break;
+    // -- legality of the current pose (sfw_planner.cpp:545-575) --
+    double sn = 0.0, cs = 1.0;
+    int fc = -1;
     if (alive) {
-      // -- legality of the current pose (sfw_planner.cpp:545-575) --
-      double sn, cs;
       sincos(th, &sn, &cs);
-      const int fc = footprint_cost(mv, s_fp, (int)F, x, y, sn, cs);
-      if (fc < 0) {
-        alive = false;
-      } else {
+      fc = footprint_cost(mv, s_fp, (int)F, x, y, sn, cs);
+    }
+    // The Bresenham loops above leave the warp split; without this the whole social-force step
+    // below would run once per fragment (measured: 19.8 of 32 lanes active, profiles/r1a).
+    __syncwarp();
+    if (fc < 0)
+      alive = false;
+    if (alive) {
+      {
         costmap_sum = __dadd_rn(costmap_sum, __ddiv_rn((double)fc, 255.0));
         ++npts;
         // -- velocities and pose (sfw_planner.cpp:581-588, hpp:418-463) --
@@ -502,20 +515,22 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
           float2 fa = fr[a * T];
           float fx, fy, fm;
           // pedestrian a <- robot (robot at the pose the previous step left it)
-          pair_force(K, A.x, A.y, A.z, A.w, prx, pry, rvxf, rvyf, fx, fy, fm);
+          pair_force<true>(K, A.x, A.y, A.z, A.w, prx, pry, rvxf, rvyf, fx, fy, fm);
           fa.x += fx;
           fa.y += fy;
           rfx -= fx;
           rfy -= fy;
           wp += fm; // = computeSocialWork's per-pedestrian term of the PREVIOUS step
+#pragma unroll 2
           for (uint32_t b = a + 1; b < P; ++b) {
             const float4 Bs = st[b * T];
-            pair_force(K, A.x, A.y, A.z, A.w, Bs.x, Bs.y, Bs.z, Bs.w, fx, fy, fm);
-            fa.x += fx;
-            fa.y += fy;
+            float gx_, gy_, gm_;
+            pair_force<false>(K, A.x, A.y, A.z, A.w, Bs.x, Bs.y, Bs.z, Bs.w, gx_, gy_, gm_);
+            fa.x += gx_;
+            fa.y += gy_;
             float2 fb = fr[b * T];
-            fb.x -= fx;
-            fb.y -= fy;
+            fb.x -= gx_;
+            fb.y -= gy_;
             fr[b * T] = fb;
           }
           // obstacle force
@@ -584,7 +599,7 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
     for (uint32_t a = 0; a < P; ++a) {
       const float4 A = st[a * T];
       float fx, fy, fm;
-      pair_force(K, A.x, A.y, A.z, A.w, prx, pry, rvxf, rvyf, fx, fy, fm);
+      pair_force<true>(K, A.x, A.y, A.z, A.w, prx, pry, rvxf, rvyf, fx, fy, fm);
       wp += fm;
     }
     social_work += (double)wp;
