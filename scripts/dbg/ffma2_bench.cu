@@ -1,0 +1,86 @@
+// Microbenchmark: issue rate of FFMA vs FFMA2 (fma.rn.f32x2) vs MUFU on sm_100a.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o ffma2_bench ffma2_bench.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float fma1(float a, float b, float c) {
+  float r;
+  asm volatile("fma.rn.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+template <int MODE> __global__ void k(float *out, int iters, float a, float b) {
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = threadIdx.x * 0.001f + i;
+  u64 pa, pb;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(pa) : "f"(a));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(pb) : "f"(b));
+  u64 p[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) asm("mov.b64 %0, {%1, %2};" : "=l"(p[i]) : "f"(acc[2 * i]), "f"(acc[2 * i + 1]));
+  for (int it = 0; it < iters; ++it) {
+    if (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = fma1(acc[i], a, b);
+    } else if (MODE == 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) p[i] = fma2(p[i], pa, pb);
+    } else if (MODE == 2) {  // 8 MUFU.EX2 + 8 FFMA
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float y;
+        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(acc[i]));
+        acc[i] = y;
+      }
+    } else if (MODE == 3) {  // mix: 1 MUFU per 4 FFMA2
+#pragma unroll
+      for (int i = 0; i < 8; ++i) p[i] = fma2(p[i], pa, pb);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float y;
+        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(acc[i]));
+        acc[i] = y;
+      }
+    }
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p[i]));
+    s += lo + hi;
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <int MODE> void run(const char *name, double ops_per_iter_per_thread) {
+  int sms = 148, blocks = sms * 4, threads = 256, iters = 20000;
+  float *out;
+  cudaMalloc(&out, blocks * threads * 4);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  k<MODE><<<blocks, threads>>>(out, 100, 1.0001f, 0.5f);
+  cudaEventRecord(e0);
+  k<MODE><<<blocks, threads>>>(out, iters, 1.0001f, 0.5f);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms;
+  cudaEventElapsedTime(&ms, e0, e1);
+  double ops = ops_per_iter_per_thread * iters * (double)blocks * threads;
+  printf("%-28s %8.3f ms  %8.2f Gop/s  = %6.1f op/clk/SM @1.965GHz\n", name, ms, ops / ms / 1e6, ops / (ms * 1e-3) / 148 / 1.965e9);
+  cudaFree(out);
+}
+int main() {
+  run<0>("FFMA (16 per iter)", 16);
+  run<1>("FFMA2 (8 per iter, 16 fma)", 16);
+  run<2>("MUFU.EX2 (8 per iter)", 8);
+  run<3>("8 FFMA2 + 2 MUFU", 18);
+  return 0;
+}

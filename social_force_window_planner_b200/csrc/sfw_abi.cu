@@ -374,8 +374,8 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     maxF = std::max(maxF, sc.n_footprint);
     max_sx = std::max(max_sx, sc.size_x);
     max_sy = std::max(max_sy, sc.size_y);
-    totP += sc.n_peds;
-    totM += align_up(sc.n_obstacles, 2); // keep every scene's obstacle block 16 B aligned
+    totP += (sc.n_peds + 1) / 2;         // pedestrians are stored as pairs
+    totM += align_up(sc.n_obstacles, 2); // obstacle lists are padded to an even count
     totF += sc.n_footprint;
   }
 
@@ -440,11 +440,15 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   size_t off = 0;
   const size_t o_scenes = off;
   off = align_up(off + sizeof(SfwSceneDev) * n_scenes, kAlign);
-  const size_t o_pedA = off;
+  const size_t o_pos = off;
   off = align_up(off + 16 * totP, kAlign);
-  const size_t o_pedB = off;
+  const size_t o_vel = off;
   off = align_up(off + 16 * totP, kAlign);
-  const size_t o_pedC = off;
+  const size_t o_goal = off;
+  off = align_up(off + 16 * totP, kAlign);
+  const size_t o_par = off;
+  off = align_up(off + 16 * totP, kAlign);
+  const size_t o_par2 = off;
   off = align_up(off + 16 * totP, kAlign);
   const size_t o_obs = off;
   off = align_up(off + 8 * totM, kAlign);
@@ -464,9 +468,11 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   // ---- pack ----------------------------------------------------------------------------------
   uint8_t *h = c->in.host;
   SfwSceneDev *hs = reinterpret_cast<SfwSceneDev *>(h + o_scenes);
-  float4 *hA = reinterpret_cast<float4 *>(h + o_pedA);
-  float4 *hB = reinterpret_cast<float4 *>(h + o_pedB);
-  float4 *hC = reinterpret_cast<float4 *>(h + o_pedC);
+  float4 *hPos = reinterpret_cast<float4 *>(h + o_pos);
+  float4 *hVel = reinterpret_cast<float4 *>(h + o_vel);
+  float4 *hGoal = reinterpret_cast<float4 *>(h + o_goal);
+  float4 *hPar = reinterpret_cast<float4 *>(h + o_par);
+  float4 *hPar2 = reinterpret_cast<float4 *>(h + o_par2);
   float2 *hO = reinterpret_cast<float2 *>(h + o_obs);
   double2 *hF = reinterpret_cast<double2 *>(h + o_fp);
   memcpy(h + o_lin, linvels, 8 * (size_t)n_v);
@@ -500,30 +506,57 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     d.size_y = sc.size_y;
     d.win_x0 = wx0[s];
     d.win_y0 = wy0[s];
+    const uint32_t n_pairs = (sc.n_peds + 1) / 2;
+    const uint32_t n_obst_pad = (uint32_t)align_up(sc.n_obstacles, 2);
     d.n_peds = sc.n_peds;
-    d.n_obst = sc.n_obstacles;
+    d.n_pairs = n_pairs;
+    d.n_obst = n_obst_pad;
     d.n_fp = sc.n_footprint;
     d.ped_off = pP;
     d.obs_off = pM;
     d.fp_off = pF;
     d.map_off = slot * s;
-    for (uint32_t j = 0; j < sc.n_peds; ++j) {
-      const SfwPed &p = sc.peds[j];
-      hA[pP + j] = make_float4((float)(p.x - R.x), (float)(p.y - R.y), (float)p.vx, (float)p.vy);
-      hB[pP + j] = make_float4((float)(p.goal_x - R.x), (float)(p.goal_y - R.y),
-                               (float)(p.goal_radius * p.goal_radius), (float)p.desired_velocity);
-      hC[pP + j] = make_float4((float)(obs_norm * std::exp(p.radius * inv_sigma)),
-                               p.has_goal ? 1.0f : 0.0f,
-                               (float)(p.desired_velocity * p.desired_velocity), (float)p.group_id);
+    d.goal_mask = 0;
+    // Pedestrian pair (2k, 2k+1): one float4 per quantity = (q0, q1) x (x, y).  An odd crowd is padded
+    // with an agent SFW_FAR_AWAY from everything: all its pair/obstacle terms underflow to exactly 0.
+    for (uint32_t k = 0; k < n_pairs; ++k) {
+      float q[2][10];
+      for (uint32_t hlf = 0; hlf < 2; ++hlf) {
+        const uint32_t j = 2 * k + hlf;
+        float *v = q[hlf];
+        if (j < sc.n_peds) {
+          const SfwPed &p = sc.peds[j];
+          v[0] = (float)(p.x - R.x);
+          v[1] = (float)(p.y - R.y);
+          v[2] = (float)p.vx;
+          v[3] = (float)p.vy;
+          v[4] = (float)(p.goal_x - R.x);
+          v[5] = (float)(p.goal_y - R.y);
+          v[6] = (float)(p.goal_radius * p.goal_radius);
+          v[7] = (float)p.desired_velocity;
+          v[8] = (float)(obs_norm * std::exp(p.radius * inv_sigma));
+          v[9] = (float)(p.desired_velocity * p.desired_velocity);
+          if (p.has_goal)
+            d.goal_mask |= (1ull << j);
+        } else {
+          v[0] = v[4] = SFW_FAR_AWAY;
+          v[1] = v[2] = v[3] = v[5] = v[6] = v[7] = v[8] = v[9] = 0.f;
+        }
+      }
+      hPos[pP + k] = make_float4(q[0][0], q[1][0], q[0][1], q[1][1]);
+      hVel[pP + k] = make_float4(q[0][2], q[1][2], q[0][3], q[1][3]);
+      hGoal[pP + k] = make_float4(q[0][4], q[1][4], q[0][5], q[1][5]);
+      hPar[pP + k] = make_float4(q[0][6], q[1][6], q[0][7], q[1][7]);
+      hPar2[pP + k] = make_float4(q[0][8], q[1][8], q[0][9], q[1][9]);
     }
-    pP += sc.n_peds;
-    // obstacle points: scene frame, pre-multiplied by log2(e)/sigma (see obstacle_sum)
+    pP += n_pairs;
+    // obstacle points: scene frame, pre-multiplied by log2(e)/sigma (see obstacle_sum2)
     for (uint32_t k = 0; k < sc.n_obstacles; ++k)
       hO[pM + k] = make_float2((float)((sc.obstacles_xy[2 * k] - R.x) * c_obs_d),
                                (float)((sc.obstacles_xy[2 * k + 1] - R.y) * c_obs_d));
     if (sc.n_obstacles & 1u)
-      hO[pM + sc.n_obstacles] = make_float2(0.f, 0.f);
-    pM += (uint32_t)align_up(sc.n_obstacles, 2);
+      hO[pM + sc.n_obstacles] = make_float2(SFW_FAR_AWAY, 0.f);
+    pM += n_obst_pad;
     for (uint32_t k = 0; k < sc.n_footprint; ++k)
       hF[pF + k] = make_double2(sc.footprint_xy[2 * k], sc.footprint_xy[2 * k + 1]);
     pF += sc.n_footprint;
@@ -570,9 +603,11 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   memset(&B, 0, sizeof(B));
   uint8_t *dv = c->in.dev;
   B.scenes = reinterpret_cast<const SfwSceneDev *>(dv + o_scenes);
-  B.pedA = reinterpret_cast<const float4 *>(dv + o_pedA);
-  B.pedB = reinterpret_cast<const float4 *>(dv + o_pedB);
-  B.pedC = reinterpret_cast<const float4 *>(dv + o_pedC);
+  B.pedPos = reinterpret_cast<const float4 *>(dv + o_pos);
+  B.pedVel = reinterpret_cast<const float4 *>(dv + o_vel);
+  B.pedGoal = reinterpret_cast<const float4 *>(dv + o_goal);
+  B.pedPar = reinterpret_cast<const float4 *>(dv + o_par);
+  B.pedPar2 = reinterpret_cast<const float4 *>(dv + o_par2);
   B.obst = reinterpret_cast<const float2 *>(dv + o_obs);
   B.footprint = reinterpret_cast<const double2 *>(dv + o_fp);
   B.maps = dv + o_maps;

@@ -16,6 +16,7 @@
 #include "../../include/sfw_b200.h"
 
 #define SFW_MAX_PEDS_SMALL 64 /* thread-per-trajectory kernel: goal flags live in one 64-bit mask */
+#define SFW_FAR_AWAY 1.0e15f  /* padding pedestrian / obstacle: every force term underflows to exactly 0 */
 #define SFW_MAX_FOOTPRINT 64
 #define SFW_MAX_BLOCK_SMALL 512 /* launch bound of the thread-per-trajectory kernel (128 regs/thread) */
 
@@ -30,10 +31,11 @@ struct SfwSceneDev {
   float a_obs_scale; // (k_obs / M) * exp(agent_radius / sigma)
   uint32_t size_x, size_y;
   int32_t win_x0, win_y0; // first cell of the staged window (may be negative / beyond the map)
-  uint32_t n_peds, n_obst, n_fp;
-  uint32_t ped_off, obs_off, fp_off; // element offsets into the packed arrays
-  uint32_t pad0;
+  uint32_t n_peds, n_obst, n_fp; // n_obst: padded to an even count with a far-away point
+  uint32_t ped_off, obs_off, fp_off; // element offsets into the packed arrays (ped_off in PAIRS)
+  uint32_t n_pairs;                  // ceil(n_peds / 2); an odd crowd is padded with a far-away agent
   uint64_t map_off; // byte offset of this scene's costmap slot
+  uint64_t goal_mask; // bit j: pedestrian j has a goal (sfm::Agent::goals non-empty)
 };
 
 struct SfwBlockBest {
@@ -43,10 +45,14 @@ struct SfwBlockBest {
 
 struct SfwBatchDev {
   const SfwSceneDev *scenes;
-  const float4 *pedA; // x, y, vx, vy            (scene frame)
-  const float4 *pedB; // goal_x, goal_y, goal_r^2, desired_velocity
-  const float4 *pedC; // obs_scale, has_goal (0/1), desired_velocity^2, group id (as float)
-  const float2 *obst; // obstacle points (scene frame)
+  // pedestrians are stored as PAIRS (2k, 2k+1), one float4 per pair and quantity, so that the two
+  // halves of a packed FP32x2 register pair load with one LDS.128 (scene frame, FP32):
+  const float4 *pedPos;  // x0, x1, y0, y1
+  const float4 *pedVel;  // vx0, vx1, vy0, vy1
+  const float4 *pedGoal; // gx0, gx1, gy0, gy1
+  const float4 *pedPar;  // goal_r^2 (0,1), desired_velocity (0,1)
+  const float4 *pedPar2; // obs_scale (0,1), desired_velocity^2 (0,1)
+  const float2 *obst; // obstacle points (scene frame) * log2(e)/sigma
   const double2 *footprint;
   const uint8_t *maps; // costmap slots: map_rows rows of map_pitch bytes each
   const double *linvels;

@@ -117,29 +117,86 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Packed FP32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2): two independent force evaluations
+// ride in the two halves of a 64-bit register pair.  Measured on B200 (scripts/dbg/ffma2_bench.cu):
+// FFMA2 sustains the same 128 FMA/clk/SM as FFMA with HALF the issue slots, which is what this
+// issue-bound kernel needs.  MUFU, min/max and selects stay scalar per half.
+// ------------------------------------------------------------------------------------------------
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 mk2(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f2 bc2(float a) { return mk2(a, a); }
+__device__ __forceinline__ void un2(f2 a, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+  f2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f2 rsqrt2(f2 a) {
+  float lo, hi;
+  un2(a, lo, hi);
+  return mk2(rsqrt_approx(lo), rsqrt_approx(hi));
+}
+
+// ------------------------------------------------------------------------------------------------
 // lightsfm pair social force in FP32.  Force on agent a from agent b, already
-// scaled by forceFactorSocial.  e_ang is the magnitude of the angular term, used for |F|.
+// scaled by forceFactorSocial.
+//
+// theta (angle from interactionDirection i to diffDirection e) is needed only as theta^2 plus its
+// sign.  With I = lambda*vd + e (unnormalised), L = |I|:  I x e = lambda * (vd x e)  exactly, so the
+// sine is formed from the velocity difference — no cancellation, and EXACTLY zero when the two
+// velocities are equal, where lightsfm gets theta == 0 and switches the angular term off.
+// |theta| = asin(min(|sin|,|cos|)) folded back by quadrant; asin on [0, 1/sqrt 2] is an 8-term odd
+// minimax polynomial (|err| < 1e-7, fit in DESIGN.md), so no division and one MUFU less than atan2.
 // ------------------------------------------------------------------------------------------------
 struct SfmConst {
   float lambda, c_d, g2, c_np, c_n, k_soc; // g2 = gamma^2
 };
 
-// atan(t) for t in [0,1]: odd minimax polynomial, |err| < 1e-7 in FP32 (fit in DESIGN.md)
-__device__ __forceinline__ float atan01(float t) {
-  const float u = t * t;
-  float p = 0.0024567015934735537f;
-  p = fmaf(p, u, -0.01440125796943903f);
-  p = fmaf(p, u, 0.03978104144334793f);
-  p = fmaf(p, u, -0.07234840095043182f);
-  p = fmaf(p, u, 0.10498936474323273f);
-  p = fmaf(p, u, -0.14161226153373718f);
-  p = fmaf(p, u, 0.19985906779766083f);
-  p = fmaf(p, u, -0.33332598209381104f);
-  p = fmaf(p, u, 0.9999998807907104f);
-  return p * t;
+#define SFW_ASIN_C0 0.9999998211860657f
+#define SFW_ASIN_C1 0.16668058931827545f
+#define SFW_ASIN_C2 0.0746382400393486f
+#define SFW_ASIN_C3 0.04882850497961044f
+#define SFW_ASIN_C4 0.005111650098115206f
+#define SFW_ASIN_C5 0.10628256946802139f
+#define SFW_ASIN_C6 -0.13144730031490326f
+#define SFW_ASIN_C7 0.13190637528896332f
+
+// quadrant fold: phi = asin(min(|s|,|c|)) in [0, pi/4] -> |theta| in [0, pi]
+__device__ __forceinline__ float fold_theta(float phi, float asn, float acs, float cs) {
+  float th = (asn > acs) ? (1.5707963267948966f - phi) : phi;
+  return (cs < 0.0f) ? (3.14159265358979f - th) : th;
+}
+// -sign(theta) * mag with lightsfm's Angle::sign(): 0 only for theta == 0, +1 for theta == pi
+// (mag may carry any sign; only its magnitude is used)
+__device__ __forceinline__ float signed_angle_term(float mag, float sn, float cs) {
+  float fa = __uint_as_float((__float_as_uint(mag) & 0x7fffffffu) | (__float_as_uint(sn) & 0x80000000u));
+  if (sn == 0.0f)
+    fa = (cs < 0.0f) ? fabsf(mag) : 0.0f;
+  return fa; // = +sign(theta) * |mag|
 }
 
-// WITH_MAG: also return |F| (only the robot-pedestrian pairs need it, for the social work).
+// scalar version (diagonal pairs, last-step pass)
 template <bool WITH_MAG>
 __device__ __forceinline__ void pair_force(const SfmConst &K, float ax, float ay, float avx,
                                            float avy, float bx, float by, float bvx, float bvy,
@@ -148,59 +205,144 @@ __device__ __forceinline__ void pair_force(const SfmConst &K, float ax, float ay
   const float d2 = fmaf(dx, dx, fmaf(dy, dy, 1e-30f));    // +eps: coincident agents give 0, not NaN
   const float rd = rsqrt_approx(d2);
   const float ex = dx * rd, ey = dy * rd;                 // diffDirection
-  const float ix = fmaf(K.lambda, avx - bvx, ex);         // interactionVector
-  const float iy = fmaf(K.lambda, avy - bvy, ey);
+  const float vdx = avx - bvx, vdy = avy - bvy;
+  const float ix = fmaf(K.lambda, vdx, ex);               // interactionVector
+  const float iy = fmaf(K.lambda, vdy, ey);
   const float L2 = fmaf(ix, ix, fmaf(iy, iy, 1e-30f));
   const float rL = rsqrt_approx(L2);                      // 1 / interactionLength
-  // theta = angle from interactionDirection to diffDirection = atan2(i x e, i . e).  The cross
-  // product is a difference of two ROUNDED products (no FMA) so that equal velocities (i == e
-  // bit for bit) give exactly theta = 0 and no angular term, as lightsfm's Angle::sign() does.
-  const float sn = __fsub_rn(__fmul_rn(ix, ey), __fmul_rn(iy, ex));
-  const float cs = fmaf(ix, ex, iy * ey);
+  const float sn = K.lambda * fmaf(vdx, ey, -(vdy * ex)); // I x e
+  const float cs = fmaf(ix, ex, iy * ey);                 // I . e
   const float asn = fabsf(sn), acs = fabsf(cs);
-  const float mx = fmaxf(asn, acs), mn = fminf(asn, acs);
-  float th = atan01(mn * rcp_approx(fmaxf(mx, 1e-30f)));
-  th = (asn > acs) ? (1.5707963267948966f - th) : th;
-  th = (cs < 0.0f) ? (3.14159265358979f - th) : th;       // |theta| in [0, pi]
+  const float m = fminf(asn, acs) * rL;
+  const float u = m * m;
+  float p = SFW_ASIN_C7;
+  p = fmaf(p, u, SFW_ASIN_C6);
+  p = fmaf(p, u, SFW_ASIN_C5);
+  p = fmaf(p, u, SFW_ASIN_C4);
+  p = fmaf(p, u, SFW_ASIN_C3);
+  p = fmaf(p, u, SFW_ASIN_C2);
+  p = fmaf(p, u, SFW_ASIN_C1);
+  p = fmaf(p, u, SFW_ASIN_C0);
+  const float th = fold_theta(p * m, asn, acs, cs);
   const float q = (K.g2 * L2) * (th * th);                // (B theta)^2, B = gamma * interactionLength
   const float t = -((d2 * rd) * rL) * K.c_d;              // -|diff| / B  (in log2 units)
   const float e_vel = ex2_approx(fmaf(-K.c_np, q, t));    // exp(-d/B - (n' B theta)^2)
   const float e_ang = ex2_approx(fmaf(-K.c_n, q, t));     // exp(-d/B - (n  B theta)^2)
-  const float rLk = rL * K.k_soc;
-  const float fv = e_vel * rLk;                           // -(force along interactionVector)
-  // forceAngle = -sign(theta) * e_ang along the left normal.  sign(theta) is 0 only for theta == 0
-  // exactly; theta == pi counts as positive (lightsfm Angle wraps to (-pi, pi]).
-  float fa = __uint_as_float(__float_as_uint(e_ang * rLk) | (__float_as_uint(sn) & 0x80000000u));
-  if (sn == 0.0f)
-    fa = (cs < 0.0f) ? fabsf(fa) : 0.0f;                  // here fa = +sign(theta) * magnitude
-  // F = -fv * i - fa * leftNormal(i), leftNormal(i) = (-iy, ix)
-  fx = fmaf(fa, iy, -(fv * ix));
-  fy = -fmaf(fa, ix, fv * iy);
+  const float rLkn = rL * -K.k_soc;
+  const float fvn = e_vel * rLkn;                         // force along interactionVector (negative)
+  const float fa = signed_angle_term(e_ang * rLkn, sn, cs);
+  // F = fvn * I - fa * leftNormal(I), leftNormal(I) = (-iy, ix)
+  fx = fmaf(fa, iy, fvn * ix);
+  fy = fmaf(-fa, ix, fvn * iy);
   if (WITH_MAG) {
     const float ea = (sn == 0.0f && cs >= 0.0f) ? 0.0f : e_ang;
     fmag = K.k_soc * sqrt_approx(fmaf(e_vel, e_vel, ea * ea));
   }
 }
 
+// packed version: two (a, b) evaluations at once, one per register half
+template <bool WITH_MAG>
+__device__ __forceinline__ void pair_force2(const SfmConst &K, f2 ax, f2 ay, f2 avx, f2 avy, f2 bx,
+                                            f2 by, f2 bvx, f2 bvy, f2 &fx, f2 &fy, f2 &fmag) {
+  const f2 eps = bc2(1e-30f);
+  const f2 dx = sub2(bx, ax), dy = sub2(by, ay);
+  const f2 d2 = fma2(dx, dx, fma2(dy, dy, eps));
+  const f2 rd = rsqrt2(d2);
+  const f2 ex = mul2(dx, rd), ey = mul2(dy, rd);
+  const f2 vdx = sub2(avx, bvx), vdy = sub2(avy, bvy);
+  const f2 lam = bc2(K.lambda);
+  const f2 ix = fma2(lam, vdx, ex), iy = fma2(lam, vdy, ey);
+  const f2 L2 = fma2(ix, ix, fma2(iy, iy, eps));
+  const f2 rL = rsqrt2(L2);
+  const f2 sn = mul2(lam, sub2(mul2(vdx, ey), mul2(vdy, ex)));
+  const f2 cs = fma2(ix, ex, mul2(iy, ey));
+  float sn0, sn1, cs0, cs1;
+  un2(sn, sn0, sn1);
+  un2(cs, cs0, cs1);
+  const float asn0 = fabsf(sn0), asn1 = fabsf(sn1), acs0 = fabsf(cs0), acs1 = fabsf(cs1);
+  const f2 m = mul2(mk2(fminf(asn0, acs0), fminf(asn1, acs1)), rL);
+  const f2 u = mul2(m, m);
+  f2 p = bc2(SFW_ASIN_C7);
+  p = fma2(p, u, bc2(SFW_ASIN_C6));
+  p = fma2(p, u, bc2(SFW_ASIN_C5));
+  p = fma2(p, u, bc2(SFW_ASIN_C4));
+  p = fma2(p, u, bc2(SFW_ASIN_C3));
+  p = fma2(p, u, bc2(SFW_ASIN_C2));
+  p = fma2(p, u, bc2(SFW_ASIN_C1));
+  p = fma2(p, u, bc2(SFW_ASIN_C0));
+  float ph0, ph1;
+  un2(mul2(p, m), ph0, ph1);
+  const f2 th = mk2(fold_theta(ph0, asn0, acs0, cs0), fold_theta(ph1, asn1, acs1, cs1));
+  const f2 q = mul2(mul2(bc2(K.g2), L2), mul2(th, th));
+  const f2 t = mul2(mul2(mul2(d2, rd), rL), bc2(-K.c_d));
+  float a0, a1, b0, b1;
+  un2(fma2(bc2(-K.c_np), q, t), a0, a1);
+  un2(fma2(bc2(-K.c_n), q, t), b0, b1);
+  const float ev0 = ex2_approx(a0), ev1 = ex2_approx(a1);
+  const float ea0 = ex2_approx(b0), ea1 = ex2_approx(b1);
+  const f2 rLkn = mul2(rL, bc2(-K.k_soc));
+  const f2 fvn = mul2(mk2(ev0, ev1), rLkn);
+  float m0, m1;
+  un2(mul2(mk2(ea0, ea1), rLkn), m0, m1);
+  const f2 fa = mk2(signed_angle_term(m0, sn0, cs0), signed_angle_term(m1, sn1, cs1));
+  fx = fma2(fa, iy, mul2(fvn, ix));
+  fy = sub2(mul2(fvn, iy), mul2(fa, ix));
+  if (WITH_MAG) {
+    const float z0 = (sn0 == 0.0f && cs0 >= 0.0f) ? 0.0f : ea0;
+    const float z1 = (sn1 == 0.0f && cs1 >= 0.0f) ? 0.0f : ea1;
+    fmag = mk2(K.k_soc * sqrt_approx(fmaf(ev0, ev0, z0 * z0)), K.k_soc * sqrt_approx(fmaf(ev1, ev1, z1 * z1)));
+  }
+}
+
 // lightsfm obstacle force sum (unscaled): sum_o exp(-|p-o|/sigma) (p-o)/|p-o|.  Obstacle points are
 // stored pre-multiplied by c_obs = log2(e)/sigma, and so is the query point: then |p'-o'| is the
-// exponent in log2 units and the unit vector is unchanged.
-__device__ __forceinline__ void obstacle_sum(const float2 *__restrict__ obs, int M, float c_obs,
-                                             float px, float py, float &sx, float &sy) {
-  float ax = 0.f, ay = 0.f;
-  const float qx = px * c_obs, qy = py * c_obs;
+// exponent in log2 units and the unit vector is unchanged.  The list is padded to an even count
+// with a point 1e15 away, whose term is exactly 0 (ex2 underflows).
+// (a) two query points (a pedestrian pair) against every obstacle
+__device__ __forceinline__ void obstacle_sum2(const float2 *__restrict__ obs, int M, float c_obs, f2 px,
+                                              f2 py, f2 &sx, f2 &sy) {
+  f2 ax = bc2(0.f), ay = bc2(0.f);
+  const f2 eps = bc2(1e-30f);
+  const f2 qx = mul2(px, bc2(c_obs)), qy = mul2(py, bc2(c_obs));
 #pragma unroll 4
   for (int o = 0; o < M; ++o) {
     const float2 p = obs[o];
-    const float dx = qx - p.x, dy = qy - p.y;
-    const float d2 = fmaf(dx, dx, fmaf(dy, dy, 1e-30f));
-    const float rd = rsqrt_approx(d2);
-    const float e = ex2_approx(-(d2 * rd)) * rd;
-    ax = fmaf(e, dx, ax);
-    ay = fmaf(e, dy, ay);
+    const f2 dx = sub2(qx, bc2(p.x)), dy = sub2(qy, bc2(p.y));
+    const f2 d2 = fma2(dx, dx, fma2(dy, dy, eps));
+    const f2 rd = rsqrt2(d2);
+    float d0, d1;
+    un2(mul2(d2, rd), d0, d1);
+    const f2 e = mul2(mk2(ex2_approx(-d0), ex2_approx(-d1)), rd);
+    ax = fma2(e, dx, ax);
+    ay = fma2(e, dy, ay);
   }
   sx = ax;
   sy = ay;
+}
+// (b) one query point (the robot) against two obstacles per iteration
+__device__ __forceinline__ void obstacle_sum1(const float2 *__restrict__ obs, int M, float c_obs,
+                                              float px, float py, float &sx, float &sy) {
+  f2 ax = bc2(0.f), ay = bc2(0.f);
+  const f2 eps = bc2(1e-30f);
+  const f2 qx = bc2(px * c_obs), qy = bc2(py * c_obs);
+  const float4 *__restrict__ obs4 = reinterpret_cast<const float4 *>(obs);
+#pragma unroll 2
+  for (int o = 0; o < M / 2; ++o) {
+    const float4 p = obs4[o];
+    const f2 dx = sub2(qx, mk2(p.x, p.z)), dy = sub2(qy, mk2(p.y, p.w));
+    const f2 d2 = fma2(dx, dx, fma2(dy, dy, eps));
+    const f2 rd = rsqrt2(d2);
+    float d0, d1;
+    un2(mul2(d2, rd), d0, d1);
+    const f2 e = mul2(mk2(ex2_approx(-d0), ex2_approx(-d1)), rd);
+    ax = fma2(e, dx, ax);
+    ay = fma2(e, dy, ay);
+  }
+  float x0, x1, y0, y1;
+  un2(ax, x0, x1);
+  un2(ay, y0, y1);
+  sx = x0 + x1;
+  sy = y0 + y1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -209,7 +351,7 @@ __device__ __forceinline__ void obstacle_sum(const float2 *__restrict__ obs, int
 struct MapView {
   const uint8_t *win;   // staged window in shared memory (or nullptr)
   const uint8_t *glob;  // this scene's costmap slot in HBM
-  double ox, oy, res;
+  double ox, oy, res, rinv; // rinv = fl(1 / res)
   uint32_t sx, sy, pitch;
   int32_t wx0, wy0;
   uint32_t wwp, wh;     // window pitch / rows
@@ -222,53 +364,72 @@ __device__ __forceinline__ uint32_t cell_cost(const MapView &m, int cx, int cy) 
   return __ldg(m.glob + (size_t)cy * m.pitch + cx);
 }
 
-// nav2 Costmap2D::worldToMap [external, SURVEY.md App. C]; no FMA contraction, true division
+// trunc(fl(a / res)) exactly as the reference's division produces it, without dividing:
+// q = a * fl(1/res) is within |q| * 2^-51 of fl(a / res); unless q sits that close to an integer
+// the truncations agree.  The (measure ~2^-19) near-integer case and huge quotients take the
+// correctly rounded division.
+__device__ __forceinline__ unsigned int cell_index(double a, double res, double rinv) {
+  const double q = __dmul_rn(a, rinv);
+  if (q < 1073741824.0) {
+    const int i = __double2int_rz(q);
+    const double f = __dsub_rn(q, (double)i);
+    if (f > 9.5367431640625e-07 && f < 0.99999904632568359375)
+      return (unsigned int)i;
+  }
+  const double e = __ddiv_rn(a, res);
+  return e < 4294967296.0 ? (unsigned int)e : 0xffffffffu;
+}
+
+// nav2 Costmap2D::worldToMap [external, SURVEY.md App. C]; no FMA contraction
 __device__ __forceinline__ bool world_to_map(const MapView &m, double wx, double wy, int &mx, int &my) {
   if (wx < m.ox || wy < m.oy)
     return false;
-  const unsigned int ux = (unsigned int)__ddiv_rn(__dsub_rn(wx, m.ox), m.res);
-  const unsigned int uy = (unsigned int)__ddiv_rn(__dsub_rn(wy, m.oy), m.res);
+  const unsigned int ux = cell_index(__dsub_rn(wx, m.ox), m.res, m.rinv);
+  const unsigned int uy = cell_index(__dsub_rn(wy, m.oy), m.res, m.rinv);
   mx = (int)ux;
   my = (int)uy;
   return ux < m.sx && uy < m.sy;
 }
 
-// CostmapModel::lineCost over LineIterator (costmap_model.cpp:95-110, line_iterator.hpp:37-97).
-// Returns the max cell cost, or -1 when a 254/255 cell is met.
-__device__ __forceinline__ int line_cost(const MapView &m, int x0, int y0, int x1, int y1) {
-  const int deltax = abs(x1 - x0), deltay = abs(y1 - y0);
-  int xinc1 = (x1 >= x0) ? 1 : -1, xinc2 = xinc1;
-  int yinc1 = (y1 >= y0) ? 1 : -1, yinc2 = yinc1;
-  int den, num, numadd, numpixels;
-  if (deltax >= deltay) {
-    xinc1 = 0;
-    yinc2 = 0;
-    den = deltax;
-    num = deltax / 2;
-    numadd = deltay;
-    numpixels = deltax;
-  } else {
-    xinc2 = 0;
-    yinc1 = 0;
-    den = deltay;
-    num = deltay / 2;
-    numadd = deltax;
-    numpixels = deltay;
-  }
-  int x = x0, y = y0, worst = 0;
-  for (int cur = 0; cur <= numpixels; ++cur) {
-    const int c = (int)cell_cost(m, x, y);
-    if (c >= 254)
-      return -1;
-    worst = max(worst, c);
-    num += numadd;
-    if (num >= den) {
-      num -= den;
-      x += xinc1;
-      y += yinc1;
+// CostmapModel::lineCost over LineIterator (costmap_model.cpp:95-110, line_iterator.hpp:37-97):
+// the max cell cost along the Bresenham line.  The reference stops at the first 254/255 cell; those
+// are the two largest values, so "max >= 254" carries the same information without a per-cell branch.
+// IN_WINDOW: both end cells (hence the whole line) lie in the staged shared-memory window.
+template <bool IN_WINDOW>
+__device__ __forceinline__ int line_max(const MapView &m, int x0, int y0, int x1, int y1) {
+  const int dx = x1 - x0, dy = y1 - y0;
+  const int adx = abs(dx), ady = abs(dy);
+  const int sx = (dx >= 0) ? 1 : -1, sy = (dy >= 0) ? 1 : -1; // line_iterator.hpp:43-61
+  const bool xmajor = adx >= ady;                              // :63
+  const int den = xmajor ? adx : ady, numadd = xmajor ? ady : adx;
+  int num = den >> 1, worst = 0;
+  if (IN_WINDOW) {
+    const int pitch = (int)m.wwp;
+    const int step_always = xmajor ? sx : sy * pitch; // (xinc2, yinc2)
+    const int step_carry = xmajor ? sy * pitch : sx;  // (xinc1, yinc1)
+    int idx = (y0 - m.wy0) * pitch + (x0 - m.wx0);
+    for (int cur = 0; cur <= den; ++cur) {
+      worst = max(worst, (int)m.win[idx]);
+      num += numadd;
+      if (num >= den) {
+        num -= den;
+        idx += step_carry;
+      }
+      idx += step_always;
     }
-    x += xinc2;
-    y += yinc2;
+  } else {
+    int x = x0, y = y0;
+    for (int cur = 0; cur <= den; ++cur) {
+      worst = max(worst, (int)cell_cost(m, x, y));
+      num += numadd;
+      if (num >= den) {
+        num -= den;
+        x += xmajor ? 0 : sx;
+        y += xmajor ? sy : 0;
+      }
+      x += xmajor ? sx : 0;
+      y += xmajor ? 0 : sy;
+    }
   }
   return worst;
 }
@@ -287,30 +448,36 @@ __device__ __forceinline__ int footprint_cost(const MapView &m, const double2 *_
   }
   int worst = 0;
   int fx0 = 0, fy0 = 0, px = 0, py = 0;
-  for (int i = 0; i < F; ++i) {
-    const double2 v = fp[i];
-    // world_model.hpp:56-59, evaluated without contraction
-    const double wx = __dadd_rn(x, __dsub_rn(__dmul_rn(v.x, cs), __dmul_rn(v.y, sn)));
-    const double wy = __dadd_rn(y, __dadd_rn(__dmul_rn(v.x, sn), __dmul_rn(v.y, cs)));
+  bool pin = false, fin = false;
+  for (int i = 0; i <= F; ++i) {
     int mx, my;
-    if (!world_to_map(m, wx, wy, mx, my))
-      return -1;
+    bool in;
+    if (i < F) {
+      const double2 v = fp[i];
+      // world_model.hpp:56-59, evaluated without contraction
+      const double wx = __dadd_rn(x, __dsub_rn(__dmul_rn(v.x, cs), __dmul_rn(v.y, sn)));
+      const double wy = __dadd_rn(y, __dadd_rn(__dmul_rn(v.x, sn), __dmul_rn(v.y, cs)));
+      if (!world_to_map(m, wx, wy, mx, my))
+        return -1;
+      in = (uint32_t)(mx - m.wx0) < m.wwp && (uint32_t)(my - m.wy0) < m.wh;
+    } else { // closing edge last -> first
+      mx = fx0;
+      my = fy0;
+      in = fin;
+    }
     if (i == 0) {
       fx0 = mx;
       fy0 = my;
+      fin = in;
     } else {
-      const int lc = line_cost(m, px, py, mx, my);
-      if (lc < 0)
-        return -1;
+      const int lc = (pin && in) ? line_max<true>(m, px, py, mx, my) : line_max<false>(m, px, py, mx, my);
       worst = max(worst, lc);
     }
     px = mx;
     py = my;
+    pin = in;
   }
-  const int lc = line_cost(m, px, py, fx0, fy0); // closing edge last -> first
-  if (lc < 0)
-    return -1;
-  return max(worst, lc);
+  return (worst >= 254) ? -1 : worst;
 }
 
 // sfw_planner.hpp:457-463
@@ -366,21 +533,26 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   const uint32_t scene = blockIdx.x / B.tiles_per_scene;
   const uint32_t tile = blockIdx.x - scene * B.tiles_per_scene;
   const SfwSceneDev *__restrict__ scp = B.scenes + scene;
-  const uint32_t P = scp->n_peds, M = scp->n_obst, F = scp->n_fp;
+  const uint32_t P2 = scp->n_pairs, M = scp->n_obst, F = scp->n_fp;
 
   // ---- shared memory carve-up -------------------------------------------------------------
-  // [window][pedA P][pedB P][pedC P][obst M (+pad)][footprint F][mbar][tile best][state P*T][force P*T]
+  // [window][pos P2][vel P2][goal P2][par P2][par2 P2][obst M][footprint F][mbar][tile best]
+  // [per-thread columns: pos P2*T | vel P2*T | force P2*T]
   const uint32_t win_bytes = B.win_wp * B.win_h; // multiple of 16
   uint8_t *s_win = smem_raw;
   uint32_t off = (win_bytes + 127u) & ~127u;
-  float4 *s_pedA = reinterpret_cast<float4 *>(smem_raw + off);
-  off += P * 16u;
-  float4 *s_pedB = reinterpret_cast<float4 *>(smem_raw + off);
-  off += P * 16u;
-  float4 *s_pedC = reinterpret_cast<float4 *>(smem_raw + off);
-  off += P * 16u;
+  float4 *s_pos0 = reinterpret_cast<float4 *>(smem_raw + off);
+  off += P2 * 16u;
+  float4 *s_vel0 = reinterpret_cast<float4 *>(smem_raw + off);
+  off += P2 * 16u;
+  float4 *s_goal = reinterpret_cast<float4 *>(smem_raw + off);
+  off += P2 * 16u;
+  float4 *s_par = reinterpret_cast<float4 *>(smem_raw + off);
+  off += P2 * 16u;
+  float4 *s_par2 = reinterpret_cast<float4 *>(smem_raw + off);
+  off += P2 * 16u;
   float2 *s_obs = reinterpret_cast<float2 *>(smem_raw + off);
-  off += ((M * 8u) + 15u) & ~15u;
+  off += M * 8u; // M is even
   double2 *s_fp = reinterpret_cast<double2 *>(smem_raw + off);
   off += F * 16u;
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + off);
@@ -388,9 +560,11 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   float *s_redc = reinterpret_cast<float *>(smem_raw + off);
   uint32_t *s_redi = reinterpret_cast<uint32_t *>(smem_raw + off + 32u * 4u);
   off += 64u * 4u;
-  float4 *s_state = reinterpret_cast<float4 *>(smem_raw + off);
-  off += P * T * 16u;
-  float2 *s_force = reinterpret_cast<float2 *>(smem_raw + off);
+  float4 *s_pos = reinterpret_cast<float4 *>(smem_raw + off);
+  off += P2 * T * 16u;
+  float4 *s_vel = reinterpret_cast<float4 *>(smem_raw + off);
+  off += P2 * T * 16u;
+  float4 *s_frc = reinterpret_cast<float4 *>(smem_raw + off);
 
   __shared__ bool s_last;
 
@@ -399,15 +573,17 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
     mbar_init(s_bar, 1);
     fence_barrier_init();
     fence_proxy_async();
-    const uint32_t obs_bytes = ((M * 8u) + 15u) & ~15u;
-    const uint32_t tx = win_bytes + 3u * P * 16u + obs_bytes + F * 16u;
+    const uint32_t obs_bytes = M * 8u;
+    const uint32_t tx = win_bytes + 5u * P2 * 16u + obs_bytes + F * 16u;
     mbar_expect_tx(s_bar, tx);
     if (win_bytes)
       tma_load_3d(s_win, &tmap, scp->win_x0, scp->win_y0, (int)scene, s_bar);
-    if (P) {
-      bulk_g2s(s_pedA, B.pedA + scp->ped_off, P * 16u, s_bar);
-      bulk_g2s(s_pedB, B.pedB + scp->ped_off, P * 16u, s_bar);
-      bulk_g2s(s_pedC, B.pedC + scp->ped_off, P * 16u, s_bar);
+    if (P2) {
+      bulk_g2s(s_pos0, B.pedPos + scp->ped_off, P2 * 16u, s_bar);
+      bulk_g2s(s_vel0, B.pedVel + scp->ped_off, P2 * 16u, s_bar);
+      bulk_g2s(s_goal, B.pedGoal + scp->ped_off, P2 * 16u, s_bar);
+      bulk_g2s(s_par, B.pedPar + scp->ped_off, P2 * 16u, s_bar);
+      bulk_g2s(s_par2, B.pedPar2 + scp->ped_off, P2 * 16u, s_bar);
     }
     if (obs_bytes)
       bulk_g2s(s_obs, B.obst + scp->obs_off, obs_bytes, s_bar);
@@ -423,6 +599,7 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   mv.ox = scp->origin_x;
   mv.oy = scp->origin_y;
   mv.res = scp->resolution;
+  mv.rinv = __ddiv_rn(1.0, scp->resolution);
   mv.sx = scp->size_x;
   mv.sy = scp->size_y;
   mv.pitch = B.map_pitch;
@@ -446,17 +623,14 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   const bool skipped = in_range && (v_s == 0.0 && w_s == 0.0); // sfw_planner.cpp:349-352
   bool alive = in_range && !skipped;
 
-  // ---- per-thread state ------------------------------------------------------------------------
-  float4 *st = s_state + tid;  // st[a*T]
-  float2 *fr = s_force + tid;  // fr[a*T]
-  for (uint32_t a = 0; a < P; ++a) {
-    st[a * T] = s_pedA[a];
-    fr[a * T] = make_float2(0.f, 0.f);
+  // ---- per-thread state: one shared-memory column per thread (conflict-free LDS.128) ------------
+  float4 *pos = s_pos + tid, *vel = s_vel + tid, *frc = s_frc + tid; // [k * T]
+  for (uint32_t k = 0; k < P2; ++k) {
+    pos[k * T] = s_pos0[k];
+    vel[k * T] = s_vel0[k];
+    frc[k * T] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  uint64_t goalmask = 0;
-  for (uint32_t a = 0; a < P; ++a)
-    if (s_pedC[a].y != 0.f)
-      goalmask |= (1ull << a);
+  uint64_t goalmask = scp->goal_mask;
 
   double x = scp->rx, y = scp->ry, th = scp->rth;
   double vx = scp->rvx, vth = scp->rvth;
@@ -507,75 +681,125 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
         th = __dadd_rn(th, __dmul_rn(vth, dt));
         const float nrx = (float)(x - base_x), nry = (float)(y - base_y);
 
-        // -- social force step (sfw_planner.cpp:592-629) --
-        float rfx = 0.f, rfy = 0.f, wp = 0.f;
+        // -- social force step (sfw_planner.cpp:592-629), pedestrians processed as pairs --
+        f2 rfx2 = bc2(0.f), rfy2 = bc2(0.f), wp2 = bc2(0.f); // robot force / social-work partial sums
         bool hit = false;
-        for (uint32_t a = 0; a < P; ++a) {
-          const float4 A = st[a * T];
-          float2 fa = fr[a * T];
-          float fx, fy, fm;
-          // pedestrian a <- robot (robot at the pose the previous step left it)
-          pair_force<true>(K, A.x, A.y, A.z, A.w, prx, pry, rvxf, rvyf, fx, fy, fm);
-          fa.x += fx;
-          fa.y += fy;
-          rfx -= fx;
-          rfy -= fy;
-          wp += fm; // = computeSocialWork's per-pedestrian term of the PREVIOUS step
-#pragma unroll 2
-          for (uint32_t b = a + 1; b < P; ++b) {
-            const float4 Bs = st[b * T];
+        const f2 RX = bc2(prx), RY = bc2(pry), RVX = bc2(rvxf), RVY = bc2(rvyf);
+        const f2 DT = bc2(dtf);
+        for (uint32_t k = 0; k < P2; ++k) {
+          const float4 pa = pos[k * T], va = vel[k * T], fa4 = frc[k * T];
+          const f2 AX = mk2(pa.x, pa.y), AY = mk2(pa.z, pa.w);
+          const f2 AVX = mk2(va.x, va.y), AVY = mk2(va.z, va.w);
+          f2 FX = mk2(fa4.x, fa4.y), FY = mk2(fa4.z, fa4.w);
+          f2 fx, fy, fm;
+          // both pedestrians of the pair <- robot (robot at the pose the previous step left it)
+          pair_force2<true>(K, AX, AY, AVX, AVY, RX, RY, RVX, RVY, fx, fy, fm);
+          FX = add2(FX, fx);
+          FY = add2(FY, fy);
+          rfx2 = sub2(rfx2, fx);
+          rfy2 = sub2(rfy2, fy);
+          wp2 = add2(wp2, fm); // = computeSocialWork's per-pedestrian terms of the PREVIOUS step
+          // the two pedestrians of the pair against each other
+          {
             float gx_, gy_, gm_;
-            pair_force<false>(K, A.x, A.y, A.z, A.w, Bs.x, Bs.y, Bs.z, Bs.w, gx_, gy_, gm_);
-            fa.x += gx_;
-            fa.y += gy_;
-            float2 fb = fr[b * T];
-            fb.x -= gx_;
-            fb.y -= gy_;
-            fr[b * T] = fb;
+            pair_force<false>(K, pa.x, pa.z, va.x, va.z, pa.y, pa.w, va.y, va.w, gx_, gy_, gm_);
+            FX = add2(FX, mk2(gx_, -gx_));
+            FY = add2(FY, mk2(gy_, -gy_));
+          }
+          // against every later pair: a0 <- (b0, b1) and a1 <- (b0, b1), antisymmetric push to b
+          const f2 A0X = bc2(pa.x), A0Y = bc2(pa.z), A0VX = bc2(va.x), A0VY = bc2(va.z);
+          const f2 A1X = bc2(pa.y), A1Y = bc2(pa.w), A1VX = bc2(va.y), A1VY = bc2(va.w);
+          f2 s0x = bc2(0.f), s0y = bc2(0.f), s1x = bc2(0.f), s1y = bc2(0.f);
+          for (uint32_t j = k + 1; j < P2; ++j) {
+            const float4 pb = pos[j * T], vb = vel[j * T];
+            const f2 BX = mk2(pb.x, pb.y), BY = mk2(pb.z, pb.w);
+            const f2 BVX = mk2(vb.x, vb.y), BVY = mk2(vb.z, vb.w);
+            f2 hx, hy, gx2, gy2, hm;
+            pair_force2<false>(K, A0X, A0Y, A0VX, A0VY, BX, BY, BVX, BVY, hx, hy, hm);
+            pair_force2<false>(K, A1X, A1Y, A1VX, A1VY, BX, BY, BVX, BVY, gx2, gy2, hm);
+            s0x = add2(s0x, hx);
+            s0y = add2(s0y, hy);
+            s1x = add2(s1x, gx2);
+            s1y = add2(s1y, gy2);
+            const float4 fb4 = frc[j * T];
+            float bx0, bx1, by0, by1;
+            un2(sub2(mk2(fb4.x, fb4.y), add2(hx, gx2)), bx0, bx1);
+            un2(sub2(mk2(fb4.z, fb4.w), add2(hy, gy2)), by0, by1);
+            frc[j * T] = make_float4(bx0, bx1, by0, by1);
+          }
+          {
+            float l0, h0, l1, h1;
+            un2(s0x, l0, h0);
+            un2(s1x, l1, h1);
+            FX = add2(FX, mk2(l0 + h0, l1 + h1));
+            un2(s0y, l0, h0);
+            un2(s1y, l1, h1);
+            FY = add2(FY, mk2(l0 + h0, l1 + h1));
           }
           // obstacle force
-          float ox, oy;
-          obstacle_sum(s_obs, (int)M, B.c_obs, A.x, A.y, ox, oy);
-          const float4 Bp = s_pedB[a];
-          const float4 Cp = s_pedC[a];
-          // desired force (App. B-1)
-          float dfx, dfy;
-          const float gx = Bp.x - A.x, gy = Bp.y - A.y;
-          const float g2 = fmaf(gx, gx, gy * gy);
-          const bool has_goal = (goalmask >> a) & 1ull;
-          if (has_goal && g2 > Bp.z) {
-            const float rg = rsqrt_approx(g2) * Bp.w;
-            dfx = B.kd_tau * fmaf(gx, rg, -A.z);
-            dfy = B.kd_tau * fmaf(gy, rg, -A.w);
-          } else {
-            dfx = -A.z * B.inv_tau;
-            dfy = -A.w * B.inv_tau;
-          }
-          const float Fx = dfx + fa.x + Cp.x * ox;
-          const float Fy = dfy + fa.y + Cp.x * oy;
+          f2 ox, oy;
+          obstacle_sum2(s_obs, (int)M, B.c_obs, AX, AY, ox, oy);
+          const float4 G = s_goal[k], Pp = s_par[k], Pc = s_par2[k];
+          // desired force (App. B-1): k_des/tau * (e_goal * v_des - v) with a live goal, else -v/tau
+          const f2 gdx = sub2(mk2(G.x, G.y), AX), gdy = sub2(mk2(G.z, G.w), AY);
+          float g20, g21;
+          un2(fma2(gdx, gdx, mul2(gdy, gdy)), g20, g21);
+          const bool hg0 = (goalmask >> (2u * k)) & 1ull, hg1 = (goalmask >> (2u * k + 1u)) & 1ull;
+          const bool go0 = hg0 && g20 > Pp.x, go1 = hg1 && g21 > Pp.y;
+          const f2 gs = mk2(go0 ? rsqrt_approx(g20) * Pp.z : 0.f, go1 ? rsqrt_approx(g21) * Pp.w : 0.f);
+          const f2 c1 = mk2(go0 ? B.kd_tau : B.inv_tau, go1 ? B.kd_tau : B.inv_tau);
+          const f2 dfx = mul2(c1, sub2(mul2(gdx, gs), AVX));
+          const f2 dfy = mul2(c1, sub2(mul2(gdy, gs), AVY));
+          const f2 OS = mk2(Pc.x, Pc.y);
+          const f2 Fx = add2(add2(dfx, FX), mul2(OS, ox));
+          const f2 Fy = add2(add2(dfy, FY), mul2(OS, oy));
           // updatePosition (App. B-5)
-          float nvx = fmaf(Fx, dtf, A.z), nvy = fmaf(Fy, dtf, A.w);
-          const float v2 = fmaf(nvx, nvx, nvy * nvy);
-          if (v2 > Cp.z) {
-            const float sc = Bp.w * rsqrt_approx(v2);
-            nvx *= sc;
-            nvy *= sc;
-          }
-          const float npx = fmaf(nvx, dtf, A.x), npy = fmaf(nvy, dtf, A.y);
-          st[a * T] = make_float4(npx, npy, nvx, nvy);
-          fr[a * T] = make_float2(0.f, 0.f);
-          if (has_goal) {
-            const float hx = Bp.x - npx, hy = Bp.y - npy;
-            if (fmaf(hx, hx, hy * hy) <= Bp.z)
-              goalmask &= ~(1ull << a);
+          f2 nvx = fma2(Fx, DT, AVX), nvy = fma2(Fy, DT, AVY);
+          float v20, v21;
+          un2(fma2(nvx, nvx, mul2(nvy, nvy)), v20, v21);
+          const f2 sc = mk2(v20 > Pc.z ? Pp.z * rsqrt_approx(v20) : 1.0f, v21 > Pc.w ? Pp.w * rsqrt_approx(v21) : 1.0f);
+          nvx = mul2(nvx, sc);
+          nvy = mul2(nvy, sc);
+          const f2 npx = fma2(nvx, DT, AX), npy = fma2(nvy, DT, AY);
+          float px0, px1, py0, py1, vx0, vx1, vy0, vy1;
+          un2(npx, px0, px1);
+          un2(npy, py0, py1);
+          un2(nvx, vx0, vx1);
+          un2(nvy, vy0, vy1);
+          pos[k * T] = make_float4(px0, px1, py0, py1);
+          vel[k * T] = make_float4(vx0, vx1, vy0, vy1);
+          frc[k * T] = make_float4(0.f, 0.f, 0.f, 0.f);
+          // goal reached -> pop (App. B-5)
+          {
+            const f2 hx = sub2(mk2(G.x, G.y), npx), hy = sub2(mk2(G.z, G.w), npy);
+            float h0, h1;
+            un2(fma2(hx, hx, mul2(hy, hy)), h0, h1);
+            if (hg0 && h0 <= Pp.x)
+              goalmask &= ~(1ull << (2u * k));
+            if (hg1 && h1 <= Pp.y)
+              goalmask &= ~(1ull << (2u * k + 1u));
           }
           // robot / pedestrian collision with the NEW robot pose (sfw_planner.cpp:613-627)
-          const float cx = nrx - npx, cy = nry - npy;
-          hit |= (fmaf(cx, cx, cy * cy) <= rr2);
+          {
+            const f2 cx = sub2(bc2(nrx), npx), cy = sub2(bc2(nry), npy);
+            float c0, c1_;
+            un2(fma2(cx, cx, mul2(cy, cy)), c0, c1_);
+            hit |= (c0 <= rr2) | (c1_ <= rr2);
+          }
+        }
+        float rfx, rfy, wp;
+        {
+          float l, h;
+          un2(rfx2, l, h);
+          rfx = l + h;
+          un2(rfy2, l, h);
+          rfy = l + h;
+          un2(wp2, l, h);
+          wp = l + h;
         }
         // robot's own obstacle force at the pose the forces were evaluated at
         float rox, roy;
-        obstacle_sum(s_obs, (int)M, B.c_obs, prx, pry, rox, roy);
+        obstacle_sum1(s_obs, (int)M, B.c_obs, prx, pry, rox, roy);
         rox *= a_obs_scale;
         roy *= a_obs_scale;
         const float wr = sqrt_approx(fmaf(rfx, rfx, rfy * rfy)) + sqrt_approx(fmaf(rox, rox, roy * roy));
@@ -595,13 +819,18 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   float cost = in_range ? (skipped ? SFW_COST_SKIPPED : SFW_COST_INVALID) : SFW_COST_SKIPPED;
   if (alive) {
     // computeSocialWork's pedestrian term of the last step (updated states, robot at final pose)
-    float wp = 0.f;
-    for (uint32_t a = 0; a < P; ++a) {
-      const float4 A = st[a * T];
-      float fx, fy, fm;
-      pair_force<true>(K, A.x, A.y, A.z, A.w, prx, pry, rvxf, rvyf, fx, fy, fm);
-      wp += fm;
+    f2 wp2 = bc2(0.f);
+    const f2 RX = bc2(prx), RY = bc2(pry), RVX = bc2(rvxf), RVY = bc2(rvyf);
+    for (uint32_t k = 0; k < P2; ++k) {
+      const float4 pa = pos[k * T], va = vel[k * T];
+      f2 fx, fy, fm;
+      pair_force2<true>(K, mk2(pa.x, pa.y), mk2(pa.z, pa.w), mk2(va.x, va.y), mk2(va.z, va.w), RX, RY, RVX,
+                        RVY, fx, fy, fm);
+      wp2 = add2(wp2, fm);
     }
+    float wp, wph;
+    un2(wp2, wp, wph);
+    wp += wph;
     social_work += (double)wp;
     const double dx = __dsub_rn(scp->wpx, x), dy = __dsub_rn(scp->wpy, y);
     const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
@@ -739,14 +968,14 @@ extern "C" __global__ void sfw_points_kernel(const __grid_constant__ SfwBatchDev
 // launch wrappers (called from sfw_abi.cu)
 // ================================================================================================
 size_t sfw_small_smem_bytes(uint32_t win_bytes, uint32_t P, uint32_t M, uint32_t F, uint32_t T) {
+  const size_t P2 = (P + 1u) / 2u, Mp = (M + 1u) & ~1u;
   size_t off = (win_bytes + 127u) & ~127u;
-  off += 3u * (size_t)P * 16u;
-  off += ((M * 8u) + 15u) & ~15u;
+  off += 5u * P2 * 16u;
+  off += Mp * 8u;
   off += (size_t)F * 16u;
   off += 16u;
   off += 64u * 4u;
-  off += (size_t)P * T * 16u;
-  off += (size_t)P * T * 8u;
+  off += 3u * P2 * T * 16u;
   return off;
 }
 
