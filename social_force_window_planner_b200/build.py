@@ -14,11 +14,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsfw_b200.so")
-SOURCES = ["sfw_kernels.cu", "sfw_abi.cu"]
-HEADERS = ["sfw_dev.h", "sfw_kernels.h", os.path.join("..", "..", "include", "sfw_b200.h")]
+SOURCES = ["sfw_kernels.cu", "sfw_crowd.cu", "sfw_abi.cu"]
+HEADERS = ["sfw_dev.h", "sfw_kernels.h", "sfw_forces.cuh", os.path.join("..", "..", "include", "sfw_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC", "--shared", "-cudart", "static", "-diag-suppress", "177",
 ]
 
 

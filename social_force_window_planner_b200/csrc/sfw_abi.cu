@@ -38,6 +38,9 @@ struct Plan {
   // result
   uint32_t T = 0, tiles = 0;
   size_t smem = 0;
+  bool crowd = false; // block-per-trajectory kernel (sfw_crowd.cu)
+  uint32_t grid = 0;
+  int steps = 0;
   bool valid = false;
 };
 
@@ -64,7 +67,7 @@ struct sfw_ctx {
   const void *tm_ptr = nullptr;
   uint32_t tm_pitch = 0, tm_rows = 0, tm_scenes = 0, tm_wp = 0, tm_h = 0;
   Plan plan;
-  size_t off_best = 0, off_costs = 0, off_npts = 0, off_bb = 0, off_cnt = 0;
+  size_t off_best = 0, off_costs = 0, off_npts = 0, off_bb = 0, off_cnt = 0, off_work = 0;
   uint32_t out_scenes = 0, out_samples = 0, out_tiles = 0;
   uint64_t launches = 0;
   uint64_t algo_bytes = 0;
@@ -168,14 +171,48 @@ const SfwSfmParams kDefaultSfm = {2.0, 10.0, 0.2, 2.1, 3.0, 2.0, 1.0, 2.0, 0.35,
 // SM under the shared-memory and register limits, then shrink the block so a single-wave launch
 // is spread evenly over all SMs.
 int make_plan(sfw_ctx *c, uint32_t n_scenes, uint32_t samples, uint32_t P, uint32_t M, uint32_t F,
-              uint32_t win_bytes) {
+              uint32_t win_bytes, int steps) {
   Plan &pl = c->plan;
   if (pl.valid && pl.n_scenes == n_scenes && pl.samples == samples && pl.maxP == P && pl.maxM == M &&
-      pl.maxF == F && pl.win_bytes == win_bytes)
+      pl.maxF == F && pl.win_bytes == win_bytes && pl.steps == steps)
     return SFW_OK;
   uint32_t bestT = 0, bestK = 0;
   size_t max_dyn = 0;
   CK(c, sfw_small_max_dynamic_smem(&max_dyn));
+  // Thread-per-trajectory needs a whole crowd in one thread's shared-memory column; it stops paying
+  // (and its 64-bit goal mask stops fitting) beyond SFW_MAX_PEDS_SMALL.  Denser crowds go to the
+  // block-per-trajectory kernel.
+  bool try_small = P <= SFW_MAX_PEDS_SMALL;
+  if (try_small && sfw_small_smem_bytes(win_bytes, P, M, F, 128) > max_dyn)
+    try_small = false; // fewer than 4 warps per SM would fit
+  if (!try_small) {
+    const size_t smem = sfw_crowd_smem_bytes(P, M, F, (uint32_t)steps);
+    int k = 0;
+    if (smem > max_dyn)
+      return fail(c, SFW_ERR_UNSUPPORTED,
+                  "scene does not fit the block-per-trajectory kernel (peds=%u steps=%d: %zu B of shared memory)",
+                  P, steps, smem);
+    CK(c, sfw_crowd_prepare(smem, &k));
+    if (k <= 0)
+      return fail(c, SFW_ERR_UNSUPPORTED, "block-per-trajectory kernel cannot be resident (peds=%u)", P);
+    const uint64_t total = (uint64_t)n_scenes * samples;
+    pl.n_scenes = n_scenes;
+    pl.samples = samples;
+    pl.maxP = P;
+    pl.maxM = M;
+    pl.maxF = F;
+    pl.win_bytes = win_bytes;
+    pl.steps = steps;
+    pl.crowd = true;
+    pl.grid = (uint32_t)std::min<uint64_t>(total, (uint64_t)c->sm_count * k);
+    pl.T = SFW_CROWD_THREADS;
+    pl.tiles = 1;
+    pl.smem = smem;
+    pl.valid = true;
+    return SFW_OK;
+  }
+  pl.crowd = false;
+  pl.steps = steps;
   for (uint32_t T = SFW_MAX_BLOCK_SMALL; T >= 32; T -= 32) {
     size_t smem = sfw_small_smem_bytes(win_bytes, P, M, F, T);
     if (smem > max_dyn)
@@ -353,9 +390,9 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     if ((sc.n_peds && !sc.peds) || (sc.n_obstacles && !sc.obstacles_xy) ||
         (sc.n_footprint && !sc.footprint_xy))
       return fail(c, SFW_ERR_ARG, "scene %u: null array with non-zero count", s);
-    if (sc.n_peds > SFW_MAX_PEDS_SMALL)
+    if (sc.n_peds > SFW_MAX_PEDS_CROWD)
       return fail(c, SFW_ERR_UNSUPPORTED, "scene %u: %u pedestrians > %d supported by this build", s,
-                  sc.n_peds, SFW_MAX_PEDS_SMALL);
+                  sc.n_peds, SFW_MAX_PEDS_CROWD);
     if (sc.n_footprint > SFW_MAX_FOOTPRINT)
       return fail(c, SFW_ERR_UNSUPPORTED, "scene %u: footprint with %u vertices > %d", s,
                   sc.n_footprint, SFW_MAX_FOOTPRINT);
@@ -450,6 +487,8 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   off = align_up(off + 16 * totP, kAlign);
   const size_t o_par2 = off;
   off = align_up(off + 16 * totP, kAlign);
+  const size_t o_gbits = off;
+  off = align_up(off + 2 * totP, kAlign);
   const size_t o_obs = off;
   off = align_up(off + 8 * totM, kAlign);
   const size_t o_fp = off;
@@ -473,6 +512,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   float4 *hGoal = reinterpret_cast<float4 *>(h + o_goal);
   float4 *hPar = reinterpret_cast<float4 *>(h + o_par);
   float4 *hPar2 = reinterpret_cast<float4 *>(h + o_par2);
+  uint8_t *hBits = h + o_gbits;
   float2 *hO = reinterpret_cast<float2 *>(h + o_obs);
   double2 *hF = reinterpret_cast<double2 *>(h + o_fp);
   memcpy(h + o_lin, linvels, 8 * (size_t)n_v);
@@ -536,9 +576,11 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
           v[7] = (float)p.desired_velocity;
           v[8] = (float)(obs_norm * std::exp(p.radius * inv_sigma));
           v[9] = (float)(p.desired_velocity * p.desired_velocity);
-          if (p.has_goal)
+          hBits[2 * (pP + k) + hlf] = p.has_goal ? 1 : 0;
+          if (p.has_goal && j < 64)
             d.goal_mask |= (1ull << j);
         } else {
+          hBits[2 * (pP + k) + hlf] = 0;
           v[0] = v[4] = SFW_FAR_AWAY;
           v[1] = v[2] = v[3] = v[5] = v[6] = v[7] = v[8] = v[9] = 0.f;
         }
@@ -574,7 +616,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
 
   // ---- outputs -------------------------------------------------------------------------------
   const uint32_t samples = n_v * n_w;
-  rc = make_plan(c, n_scenes, samples, maxP, maxM, maxF, win_wp * win_h);
+  rc = make_plan(c, n_scenes, samples, maxP, maxM, maxF, win_wp * win_h, num_steps);
   if (rc != SFW_OK)
     return rc;
   const uint32_t max_tiles = (samples + 31) / 32; // any slab / block size fits
@@ -589,6 +631,8 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   oo = align_up(oo + sizeof(SfwBlockBest) * (size_t)max_tiles * n_scenes, kAlign);
   c->off_cnt = oo;
   oo = align_up(oo + 4 * (size_t)n_scenes, kAlign);
+  c->off_work = oo;
+  oo = align_up(oo + 64, kAlign);
   rc = arena_reserve(c, c->out, oo);
   if (rc != SFW_OK)
     return rc;
@@ -608,6 +652,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   B.pedGoal = reinterpret_cast<const float4 *>(dv + o_goal);
   B.pedPar = reinterpret_cast<const float4 *>(dv + o_par);
   B.pedPar2 = reinterpret_cast<const float4 *>(dv + o_par2);
+  B.goal_bits = dv + o_gbits;
   B.obst = reinterpret_cast<const float2 *>(dv + o_obs);
   B.footprint = reinterpret_cast<const double2 *>(dv + o_fp);
   B.maps = dv + o_maps;
@@ -702,7 +747,7 @@ int sfw_run(sfw_ctx *c) {
     Plan saved = c->plan;
     c->plan.valid = false;
     int rc = make_plan(c, B.n_scenes, std::max(samples, 1u), saved.maxP, saved.maxM, saved.maxF,
-                       saved.win_bytes);
+                       saved.win_bytes, saved.steps);
     if (rc != SFW_OK)
       return rc;
     B.tiles_per_scene = c->plan.tiles;
@@ -724,10 +769,15 @@ int sfw_run(sfw_ctx *c) {
     }
     CK(c, cudaMemsetAsync(B.npts, 0, n * 2, c->stream));
   }
-  if (re > rb) {
+  if (re > rb && c->plan.crowd) {
+    CK(c, sfw_launch_crowd(B, reinterpret_cast<unsigned int *>(c->out.dev + c->off_work), c->plan.grid,
+                           c->plan.smem, c->stream));
+    c->launches += 2; // scorer + arg-min
+    c->last_kernel = "sfw_score_crowd";
+  } else if (re > rb) {
     CK(c, sfw_launch_small(B, c->tmap, c->plan.T, c->plan.smem, c->stream));
     c->launches += 1;
-    c->last_kernel = "sfw_score_small";
+    c->last_kernel = sfw_small_kernel_name(c->plan.T);
   } else {
     // empty slab: nothing to score, every scene reports "no valid trajectory"
     CK(c, cudaMemsetAsync(B.best, 0, sizeof(SfwBest) * B.n_scenes, c->stream));

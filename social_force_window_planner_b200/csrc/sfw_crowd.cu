@@ -1,0 +1,575 @@
+// sfw_crowd.cu — sm_100a kernel for dense crowds (more pedestrians than the thread-per-trajectory
+// kernel can keep in one shared-memory column): ONE BLOCK PER TRAJECTORY.
+//
+//   * persistent blocks pull (scene, sample) work items from a global counter;
+//   * prologue: the robot rollout (FP64, identical arithmetic to sfw_kernels.cu) is computed for all
+//     S steps first — it does not depend on the pedestrians — and the footprint of every (step, edge)
+//     is rasterised in parallel over the block; a trajectory the costmap rejects at step s only
+//     simulates the crowd for the s steps whose points the reference would still have recorded;
+//   * crowd step: pedestrians live in shared memory as PAIRS (packed FP32x2 layout).  Thread t owns
+//     pair t and evaluates it against the next floor((P2-1)/2) pairs in cyclic order, so every
+//     unordered pair of pairs is evaluated exactly once (lightsfm's pair force is antisymmetric) and
+//     every thread does the same amount of work.  The reaction force is pushed into a per-WARP
+//     accumulator row (lanes of a warp hit consecutive entries, rows are private to the warp, so no
+//     atomics), rows are summed after a block barrier and each thread integrates its own pair;
+//   * robot social force / social work / collision flag: warp shuffles + one shared-memory pass.
+//
+// Semantics followed: reference src/sfw_planner.cpp:475-705 (see sfw_forces.cuh for the pieces).
+#include <algorithm>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sfw_dev.h"
+#include "sfw_kernels.h"
+#include "sfw_forces.cuh"
+
+namespace {
+
+constexpr int kCrowdThreads = SFW_CROWD_THREADS;
+constexpr int kCrowdWarps = kCrowdThreads / 32;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct CrowdSmem {
+  float4 *pos, *vel, *goal, *par, *par2; // [P2]
+  float4 *frc;                           // [kCrowdWarps][P2]
+  float2 *obs;                           // [M]
+  double2 *fp;                           // [F]
+  double *rx, *ry, *rth, *rsn, *rcs;     // [S + 1] pose before step s (entry S = final pose)
+  float *rvx;                            // [S + 1] robot vx after s updates (float view for the SFM)
+  int *fcm;                              // [S] footprint max per step (>= 254: lethal, 1000: off map)
+  uint8_t *goalflag;                     // [2 * P2]
+  float *red;                            // [kCrowdWarps][4]
+  int *flags;                            // [0] work item, [1] hit, [2] first bad step
+};
+
+__device__ __forceinline__ CrowdSmem carve(unsigned char *base, uint32_t P2, uint32_t M, uint32_t F, uint32_t S) {
+  CrowdSmem s;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    unsigned char *p = base + off;
+    off += (bytes + 15u) & ~(size_t)15u;
+    return p;
+  };
+  s.pos = (float4 *)take(16u * P2);
+  s.vel = (float4 *)take(16u * P2);
+  s.goal = (float4 *)take(16u * P2);
+  s.par = (float4 *)take(16u * P2);
+  s.par2 = (float4 *)take(16u * P2);
+  s.frc = (float4 *)take(16u * P2 * kCrowdWarps);
+  s.obs = (float2 *)take(8u * M);
+  s.fp = (double2 *)take(16u * F);
+  s.rx = (double *)take(8u * (S + 1));
+  s.ry = (double *)take(8u * (S + 1));
+  s.rth = (double *)take(8u * (S + 1));
+  s.rsn = (double *)take(8u * (S + 1));
+  s.rcs = (double *)take(8u * (S + 1));
+  s.rvx = (float *)take(4u * (S + 1));
+  s.fcm = (int *)take(4u * S);
+  s.goalflag = (uint8_t *)take(2u * P2);
+  s.red = (float *)take(4u * 4u * kCrowdWarps);
+  s.flags = (int *)take(16);
+  return s;
+}
+
+} // namespace
+
+size_t sfw_crowd_smem_bytes(uint32_t P, uint32_t M, uint32_t F, uint32_t S) {
+  const size_t P2 = (P + 1u) / 2u, Mp = (M + 1u) & ~1u;
+  auto r = [](size_t b) { return (b + 15u) & ~(size_t)15u; };
+  return 5 * r(16 * P2) + r(16 * P2 * kCrowdWarps) + r(8 * Mp) + r(16 * (size_t)F) + 5 * r(8 * ((size_t)S + 1)) +
+         r(4 * ((size_t)S + 1)) + r(4 * (size_t)S) + r(2 * P2) + r(16 * kCrowdWarps) + 16;
+}
+
+// ================================================================================================
+__global__ void __launch_bounds__(SFW_CROWD_THREADS, 2)
+sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict__ work_counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t n_w = B.n_w;
+  const uint32_t per_scene = (B.row_end - B.row_begin) * n_w;
+  const uint32_t total = B.n_scenes * per_scene;
+  const int S = B.num_steps;
+  const SfmConst K = {B.lambda, B.c_d, B.gamma * B.gamma, B.c_np, B.c_n, B.k_soc};
+  const double dt = B.dt;
+  const double ax_dt = __dmul_rn(B.acc_x, dt), ath_dt = __dmul_rn(B.acc_th, dt);
+  const float dtf = B.dtf;
+  __shared__ int s_item;
+  uint32_t staged_scene = 0xffffffffu;
+
+  for (;;) {
+    __syncthreads(); // previous item fully retired before shared state is reused
+    if (tid == 0)
+      s_item = (int)atomicAdd(work_counter, 1u);
+    __syncthreads();
+    const uint32_t item = (uint32_t)s_item;
+    if (item >= total)
+      break;
+    const uint32_t scene = item / per_scene;
+    const uint32_t idx = B.row_begin * n_w + (item - scene * per_scene);
+    const SfwSceneDev *__restrict__ scp = B.scenes + scene;
+    const uint32_t P2 = scp->n_pairs, M = scp->n_obst, F = scp->n_fp;
+    const CrowdSmem sm = carve(smem_raw, P2, M, F, (uint32_t)S);
+    const double v_s = B.linvels[idx / n_w], w_s = B.angvels[idx % n_w];
+    const size_t out = (size_t)scene * B.n_v * n_w + idx;
+    if (v_s == 0.0 && w_s == 0.0) { // sfw_planner.cpp:349-352
+      if (tid == 0) {
+        B.costs[out] = SFW_COST_SKIPPED;
+        B.npts[out] = 0;
+      }
+      continue;
+    }
+
+    // ---- stage the scene (static part once per scene, state every item) ----------------------
+    for (uint32_t k = tid; k < P2; k += kCrowdThreads) {
+      sm.pos[k] = B.pedPos[scp->ped_off + k];
+      sm.vel[k] = B.pedVel[scp->ped_off + k];
+      sm.goalflag[2 * k] = B.goal_bits[2u * (scp->ped_off + k)];
+      sm.goalflag[2 * k + 1] = B.goal_bits[2u * (scp->ped_off + k) + 1u];
+      for (uint32_t w = 0; w < (uint32_t)kCrowdWarps; ++w)
+        sm.frc[w * P2 + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (staged_scene != scene) {
+      for (uint32_t k = tid; k < P2; k += kCrowdThreads) {
+        sm.goal[k] = B.pedGoal[scp->ped_off + k];
+        sm.par[k] = B.pedPar[scp->ped_off + k];
+        sm.par2[k] = B.pedPar2[scp->ped_off + k];
+      }
+      for (uint32_t o = tid; o < M; o += kCrowdThreads)
+        sm.obs[o] = B.obst[scp->obs_off + o];
+      for (uint32_t f = tid; f < F; f += kCrowdThreads)
+        sm.fp[f] = B.footprint[scp->fp_off + f];
+      staged_scene = scene;
+    }
+
+    // ---- prologue A: robot rollout, sfw_planner.cpp:581-588 (identical FP64 ops to the small kernel) ----
+    const double vy = scp->rvy;
+    if (tid == 0) { // heading and speed first: no trigonometry on this chain
+      double th = scp->rth, vx = scp->rvx, vth = scp->rvth;
+      sm.rth[0] = th;
+      sm.rvx[0] = (float)vx;
+      for (int i = 0; i < S; ++i) {
+        vx = step_velocity(v_s, vx, ax_dt);
+        vth = step_velocity(w_s, vth, ath_dt);
+        th = __dadd_rn(th, __dmul_rn(vth, dt));
+        sm.rth[i + 1] = th;
+        sm.rvx[i + 1] = (float)vx;
+        sm.rx[i + 1] = vx; // the new speed is consumed (as a double) when positions are chained below
+      }
+      sm.flags[1] = 0;
+      sm.flags[2] = S;
+    }
+    __syncthreads();
+    for (int i = (int)tid; i <= S; i += kCrowdThreads) {
+      double sn, cs;
+      sincos(sm.rth[i], &sn, &cs);
+      sm.rsn[i] = sn;
+      sm.rcs[i] = cs;
+      if (i < S)
+        sm.fcm[i] = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double x = scp->rx, y = scp->ry;
+      sm.rx[0] = x;
+      sm.ry[0] = y;
+      for (int i = 0; i < S; ++i) {
+        const double vx = sm.rx[i + 1];
+        const double sn = sm.rsn[i], cs = sm.rcs[i];
+        double lx = __dmul_rn(vx, cs), ly = __dmul_rn(vx, sn);
+        if (vy != 0.0) {
+          double sn2, cs2;
+          sincos(__dadd_rn(1.57079632679489661923, sm.rth[i]), &sn2, &cs2);
+          lx = __dadd_rn(lx, __dmul_rn(vy, cs2));
+          ly = __dadd_rn(ly, __dmul_rn(vy, sn2));
+        }
+        x = __dadd_rn(x, __dmul_rn(lx, dt));
+        y = __dadd_rn(y, __dmul_rn(ly, dt));
+        sm.rx[i + 1] = x;
+        sm.ry[i + 1] = y;
+      }
+    }
+    __syncthreads();
+
+    // ---- prologue B: footprint of every (step, edge) in parallel (sfw_planner.cpp:545-575) -------
+    MapView mv;
+    mv.win = nullptr;
+    mv.glob = B.maps + scp->map_off;
+    mv.ox = scp->origin_x;
+    mv.oy = scp->origin_y;
+    mv.res = scp->resolution;
+    mv.rinv = __ddiv_rn(1.0, scp->resolution);
+    mv.sx = scp->size_x;
+    mv.sy = scp->size_y;
+    mv.pitch = B.map_pitch;
+    mv.wx0 = 0;
+    mv.wy0 = 0;
+    mv.wwp = 0;
+    mv.wh = 0;
+    {
+      const uint32_t per_step = (F < 3u) ? 1u : F + 1u; // F edges + the centre-in-map test
+      for (uint32_t w = tid; w < (uint32_t)S * per_step; w += kCrowdThreads) {
+        const uint32_t s = w / per_step, e = w - s * per_step;
+        const double x = sm.rx[s], y = sm.ry[s], sn = sm.rsn[s], cs = sm.rcs[s];
+        int res = 0;
+        if (F < 3u || e == F) {
+          int cx, cy;
+          if (!world_to_map(mv, x, y, cx, cy))
+            res = 1000;
+          else if (F < 3u) {
+            const int c = (int)cell_cost(mv, cx, cy);
+            res = (c >= 253) ? 1000 : c;
+          }
+        } else {
+          const double2 v0 = sm.fp[e], v1 = sm.fp[(e + 1u == F) ? 0u : e + 1u];
+          int x0, y0, x1, y1;
+          const bool ok0 = world_to_map(mv, __dadd_rn(x, __dsub_rn(__dmul_rn(v0.x, cs), __dmul_rn(v0.y, sn))),
+                                        __dadd_rn(y, __dadd_rn(__dmul_rn(v0.x, sn), __dmul_rn(v0.y, cs))), x0, y0);
+          const bool ok1 = world_to_map(mv, __dadd_rn(x, __dsub_rn(__dmul_rn(v1.x, cs), __dmul_rn(v1.y, sn))),
+                                        __dadd_rn(y, __dadd_rn(__dmul_rn(v1.x, sn), __dmul_rn(v1.y, cs))), x1, y1);
+          res = (ok0 && ok1) ? line_max<false>(mv, x0, y0, x1, y1) : 1000;
+        }
+        if (res > 0)
+          atomicMax(&sm.fcm[s], res);
+      }
+    }
+    __syncthreads();
+    for (int i = (int)tid; i < S; i += kCrowdThreads)
+      if (sm.fcm[i] >= 254)
+        atomicMin(&sm.flags[2], i);
+    __syncthreads();
+    const int S_eff = sm.flags[2]; // steps whose pose is legal; < S => the trajectory is invalid
+
+    // ---- crowd simulation ---------------------------------------------------------------------
+    const double base_x = scp->rx, base_y = scp->ry;
+    const float rr2 = B.rr2;
+    const float a_obs_scale = scp->a_obs_scale;
+    double social_work = 0.0; // thread 0 only
+    const uint32_t half = P2 ? (P2 - 1u) / 2u : 0u; // full cyclic offsets
+    const bool even = P2 >= 2u && (P2 & 1u) == 0u; // + the opposite pair, first half of the ring only
+    const uint32_t owned = (P2 + kCrowdThreads - 1u) / kCrowdThreads;
+    float4 *myrow = sm.frc + warp * P2;
+    int steps_done = 0;
+    bool collided = false;
+    for (int i = 0; i < S_eff; ++i) {
+      // robot as the SFM sees it during computeForces of this step (previous pose)
+      const float prx = (i == 0) ? scp->ax : (float)(sm.rx[i] - base_x);
+      const float pry = (i == 0) ? scp->ay : (float)(sm.ry[i] - base_y);
+      const float rvxf = (i == 0) ? scp->avx : sm.rvx[i];
+      const float rvyf = (i == 0) ? scp->avy : (float)vy;
+      const float nrx = (float)(sm.rx[i + 1] - base_x), nry = (float)(sm.ry[i + 1] - base_y);
+      const f2 RX = bc2(prx), RY = bc2(pry), RVX = bc2(rvxf), RVY = bc2(rvyf);
+      f2 rfx2 = bc2(0.f), rfy2 = bc2(0.f), wp2 = bc2(0.f);
+
+      // -- phase 1: forces (sfw_planner.cpp:592) --
+      for (uint32_t m = 0; m < owned; ++m) {
+        const uint32_t a = tid + m * kCrowdThreads;
+        const bool act = a < P2;
+        float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), va = pa;
+        f2 FX = bc2(0.f), FY = bc2(0.f);
+        f2 s0x = bc2(0.f), s0y = bc2(0.f), s1x = bc2(0.f), s1y = bc2(0.f);
+        if (act) {
+          pa = sm.pos[a];
+          va = sm.vel[a];
+          f2 fx, fy, fm;
+          pair_force2<true>(K, mk2(pa.x, pa.y), mk2(pa.z, pa.w), mk2(va.x, va.y), mk2(va.z, va.w), RX, RY, RVX,
+                            RVY, fx, fy, fm);
+          FX = fx;
+          FY = fy;
+          rfx2 = sub2(rfx2, fx);
+          rfy2 = sub2(rfy2, fy);
+          wp2 = add2(wp2, fm);
+          float gx_, gy_, gm_;
+          pair_force<false>(K, pa.x, pa.z, va.x, va.z, pa.y, pa.w, va.y, va.w, gx_, gy_, gm_);
+          FX = add2(FX, mk2(gx_, -gx_));
+          FY = add2(FY, mk2(gy_, -gy_));
+        }
+        const f2 A0X = bc2(pa.x), A0Y = bc2(pa.z), A0VX = bc2(va.x), A0VY = bc2(va.z);
+        const f2 A1X = bc2(pa.y), A1Y = bc2(pa.w), A1VX = bc2(va.y), A1VY = bc2(va.w);
+        const uint32_t n_off = half + (even ? 1u : 0u);
+        for (uint32_t off = 1; off <= n_off; ++off) {
+          const bool go = act && (off <= half || a < P2 / 2u);
+          if (go) {
+            uint32_t j = a + off;
+            if (j >= P2)
+              j -= P2;
+            const float4 pb = sm.pos[j], vb = sm.vel[j];
+            const f2 BX = mk2(pb.x, pb.y), BY = mk2(pb.z, pb.w);
+            const f2 BVX = mk2(vb.x, vb.y), BVY = mk2(vb.z, vb.w);
+            f2 hx, hy, gx2, gy2, hm;
+            pair_force2<false>(K, A0X, A0Y, A0VX, A0VY, BX, BY, BVX, BVY, hx, hy, hm);
+            pair_force2<false>(K, A1X, A1Y, A1VX, A1VY, BX, BY, BVX, BVY, gx2, gy2, hm);
+            s0x = add2(s0x, hx);
+            s0y = add2(s0y, hy);
+            s1x = add2(s1x, gx2);
+            s1y = add2(s1y, gy2);
+            const float4 fb4 = myrow[j];
+            float bx0, bx1, by0, by1;
+            un2(sub2(mk2(fb4.x, fb4.y), add2(hx, gx2)), bx0, bx1);
+            un2(sub2(mk2(fb4.z, fb4.w), add2(hy, gy2)), by0, by1);
+            myrow[j] = make_float4(bx0, bx1, by0, by1);
+          }
+          __syncwarp(); // lane t+1's push to entry j lands before lane t reaches it one offset later
+        }
+        if (act) {
+          float l0, h0, l1, h1;
+          un2(s0x, l0, h0);
+          un2(s1x, l1, h1);
+          FX = add2(FX, mk2(l0 + h0, l1 + h1));
+          un2(s0y, l0, h0);
+          un2(s1y, l1, h1);
+          FY = add2(FY, mk2(l0 + h0, l1 + h1));
+          f2 ox, oy;
+          obstacle_sum2(sm.obs, (int)M, B.c_obs, mk2(pa.x, pa.y), mk2(pa.z, pa.w), ox, oy);
+          const float4 Pc = sm.par2[a];
+          const f2 OS = mk2(Pc.x, Pc.y);
+          FX = fma2(OS, ox, FX);
+          FY = fma2(OS, oy, FY);
+          const float4 own = myrow[a];
+          float x0, x1, y0, y1;
+          un2(add2(mk2(own.x, own.y), FX), x0, x1);
+          un2(add2(mk2(own.z, own.w), FY), y0, y1);
+          myrow[a] = make_float4(x0, x1, y0, y1);
+        }
+        __syncwarp();
+      }
+      {
+        float l, h;
+        un2(rfx2, l, h);
+        const float rfx = warp_sum(l + h);
+        un2(rfy2, l, h);
+        const float rfy = warp_sum(l + h);
+        un2(wp2, l, h);
+        const float wp = warp_sum(l + h);
+        if (lane == 0) {
+          sm.red[warp * 4 + 0] = rfx;
+          sm.red[warp * 4 + 1] = rfy;
+          sm.red[warp * 4 + 2] = wp;
+        }
+      }
+      __syncthreads();
+
+      // -- phase 2: updatePosition (:594), collision (:613-627), social work (:629) --
+      bool hit = false;
+      const f2 DT = bc2(dtf);
+      for (uint32_t m = 0; m < owned; ++m) {
+        const uint32_t a = tid + m * kCrowdThreads;
+        if (a >= P2)
+          break;
+        f2 FX = bc2(0.f), FY = bc2(0.f);
+        for (uint32_t w = 0; w < (uint32_t)kCrowdWarps; ++w) {
+          const float4 f = sm.frc[w * P2 + a];
+          FX = add2(FX, mk2(f.x, f.y));
+          FY = add2(FY, mk2(f.z, f.w));
+          sm.frc[w * P2 + a] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float4 pa = sm.pos[a], va = sm.vel[a];
+        const f2 AX = mk2(pa.x, pa.y), AY = mk2(pa.z, pa.w), AVX = mk2(va.x, va.y), AVY = mk2(va.z, va.w);
+        const float4 G = sm.goal[a], Pp = sm.par[a], Pc = sm.par2[a];
+        const f2 gdx = sub2(mk2(G.x, G.y), AX), gdy = sub2(mk2(G.z, G.w), AY);
+        float g20, g21;
+        un2(fma2(gdx, gdx, mul2(gdy, gdy)), g20, g21);
+        const bool hg0 = sm.goalflag[2 * a] != 0, hg1 = sm.goalflag[2 * a + 1] != 0;
+        const bool go0 = hg0 && g20 > Pp.x, go1 = hg1 && g21 > Pp.y;
+        const f2 gs = mk2(go0 ? rsqrt_approx(g20) * Pp.z : 0.f, go1 ? rsqrt_approx(g21) * Pp.w : 0.f);
+        const f2 c1 = mk2(go0 ? B.kd_tau : B.inv_tau, go1 ? B.kd_tau : B.inv_tau);
+        const f2 Fx = add2(mul2(c1, sub2(mul2(gdx, gs), AVX)), FX);
+        const f2 Fy = add2(mul2(c1, sub2(mul2(gdy, gs), AVY)), FY);
+        f2 nvx = fma2(Fx, DT, AVX), nvy = fma2(Fy, DT, AVY);
+        float v20, v21;
+        un2(fma2(nvx, nvx, mul2(nvy, nvy)), v20, v21);
+        const f2 sc = mk2(v20 > Pc.z ? Pp.z * rsqrt_approx(v20) : 1.0f, v21 > Pc.w ? Pp.w * rsqrt_approx(v21) : 1.0f);
+        nvx = mul2(nvx, sc);
+        nvy = mul2(nvy, sc);
+        const f2 npx = fma2(nvx, DT, AX), npy = fma2(nvy, DT, AY);
+        float px0, px1, py0, py1, vx0, vx1, vy0, vy1;
+        un2(npx, px0, px1);
+        un2(npy, py0, py1);
+        un2(nvx, vx0, vx1);
+        un2(nvy, vy0, vy1);
+        sm.pos[a] = make_float4(px0, px1, py0, py1);
+        sm.vel[a] = make_float4(vx0, vx1, vy0, vy1);
+        {
+          const f2 hx = sub2(mk2(G.x, G.y), npx), hy = sub2(mk2(G.z, G.w), npy);
+          float h0, h1;
+          un2(fma2(hx, hx, mul2(hy, hy)), h0, h1);
+          if (hg0 && h0 <= Pp.x)
+            sm.goalflag[2 * a] = 0;
+          if (hg1 && h1 <= Pp.y)
+            sm.goalflag[2 * a + 1] = 0;
+        }
+        {
+          const f2 cx = sub2(bc2(nrx), npx), cy = sub2(bc2(nry), npy);
+          float c0, c1_;
+          un2(fma2(cx, cx, mul2(cy, cy)), c0, c1_);
+          hit |= (c0 <= rr2) | (c1_ <= rr2);
+        }
+      }
+      if (hit)
+        sm.flags[1] = 1;
+      if (warp == 0) { // robot terms: wr from the forces of :592, wp belongs to the previous step
+        float rfx = (lane < (uint32_t)kCrowdWarps) ? sm.red[lane * 4 + 0] : 0.f;
+        float rfy = (lane < (uint32_t)kCrowdWarps) ? sm.red[lane * 4 + 1] : 0.f;
+        float wp = (lane < (uint32_t)kCrowdWarps) ? sm.red[lane * 4 + 2] : 0.f;
+        rfx = warp_sum(rfx);
+        rfy = warp_sum(rfy);
+        wp = warp_sum(wp);
+        if (lane == 0) {
+          float rox, roy;
+          obstacle_sum1(sm.obs, (int)M, B.c_obs, prx, pry, rox, roy);
+          rox *= a_obs_scale;
+          roy *= a_obs_scale;
+          const float wr = sqrt_approx(fmaf(rfx, rfx, rfy * rfy)) + sqrt_approx(fmaf(rox, rox, roy * roy));
+          social_work += (double)(wr + ((i > 0) ? wp : 0.f));
+        }
+      }
+      __syncthreads();
+      steps_done = i + 1;
+      if (sm.flags[1]) {
+        collided = true;
+        break;
+      }
+    }
+
+    // ---- terminal costs (sfw_planner.cpp:643-675) -----------------------------------------------
+    const bool valid = !collided && S_eff == S;
+    if (valid) {
+      // computeSocialWork's pedestrian term of the last step (updated states, robot at final pose)
+      const f2 RX = bc2((float)(sm.rx[S] - base_x)), RY = bc2((float)(sm.ry[S] - base_y));
+      const f2 RVX = bc2(sm.rvx[S]), RVY = bc2((float)vy);
+      f2 wp2 = bc2(0.f);
+      for (uint32_t a = tid; a < P2; a += kCrowdThreads) {
+        const float4 pa = sm.pos[a], va = sm.vel[a];
+        f2 fx, fy, fm;
+        pair_force2<true>(K, mk2(pa.x, pa.y), mk2(pa.z, pa.w), mk2(va.x, va.y), mk2(va.z, va.w), RX, RY, RVX, RVY,
+                          fx, fy, fm);
+        wp2 = add2(wp2, fm);
+      }
+      float l, h;
+      un2(wp2, l, h);
+      const float wp = warp_sum(l + h);
+      if (lane == 0)
+        sm.red[warp * 4 + 3] = wp;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float cost = SFW_COST_INVALID;
+      // points recorded: one per legal pose until the first violation (sfw_planner.cpp:578)
+      int npts = collided ? steps_done : (S_eff < S ? S_eff : S);
+      if (valid) {
+        float wp = 0.f;
+        for (int w = 0; w < kCrowdWarps; ++w)
+          wp += sm.red[w * 4 + 3];
+        social_work += (double)wp;
+        double costmap_sum = 0.0;
+        for (int i = 0; i < S; ++i)
+          costmap_sum = __dadd_rn(costmap_sum, __ddiv_rn((double)sm.fcm[i], 255.0));
+        const double x = sm.rx[S], y = sm.ry[S], th = sm.rth[S];
+        double vx = scp->rvx;
+        for (int i = 0; i < S; ++i)
+          vx = step_velocity(v_s, vx, ax_dt);
+        const double dx = __dsub_rn(scp->wpx, x), dy = __dsub_rn(scp->wpy, y);
+        const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        const double dtheta = atan2(dy, dx);
+        float angf = (float)__dsub_rn(dtheta, th);
+        angf = normalize_angle_f(angf, (float)(-M_PI), (float)M_PI);
+        const double ang_diff = __ddiv_rn(fabs((double)angf), M_PI);
+        const double vel_diff = __ddiv_rn(fabs(__dsub_rn(B.max_vel_x, vx)), B.max_vel_x);
+        const double cm = __ddiv_rn(costmap_sum, (double)S);
+        double c = __dmul_rn(B.w_vel, vel_diff);
+        c = __dadd_rn(c, __dmul_rn(B.w_dist, d));
+        c = __dadd_rn(c, __dmul_rn(B.w_ang, ang_diff));
+        c = __dadd_rn(c, __dmul_rn(B.w_map, cm));
+        c = __dadd_rn(c, __dmul_rn(B.w_soc, social_work));
+        cost = (float)c;
+      }
+      B.costs[out] = cost;
+      B.npts[out] = (uint16_t)npts;
+    }
+  }
+}
+
+// ================================================================================================
+// Arg-min of one scene's cost vector with the reference's tie-breaks (sfw_planner.cpp:394-414),
+// for the kernels that do not reduce in their own epilogue.  One block per scene.
+// ================================================================================================
+__global__ void __launch_bounds__(256) sfw_argmin_kernel(const __grid_constant__ SfwBatchDev B) {
+  const uint32_t scene = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t n_w = B.n_w, n = B.n_v * n_w;
+  const float *__restrict__ costs = B.costs + (size_t)scene * n;
+  __shared__ float s_c[8];
+  __shared__ uint32_t s_i[8];
+  float bc = -1.f;
+  uint32_t bi = 0u;
+  for (uint32_t i = B.row_begin * n_w + tid; i < B.row_end * n_w; i += 256u) {
+    const float c = costs[i];
+    if (eligible(c, B.linvels[i / n_w]) && better(c, i, bc, bi, B.linvels, B.angvels, n_w)) {
+      bc = c;
+      bi = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float oc = __shfl_xor_sync(0xffffffffu, bc, o);
+    const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(oc, oi, bc, bi, B.linvels, B.angvels, n_w)) {
+      bc = oc;
+      bi = oi;
+    }
+  }
+  if (lane == 0) {
+    s_c[warp] = bc;
+    s_i[warp] = bi;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    bc = (lane < 8u) ? s_c[lane] : -1.f;
+    bi = (lane < 8u) ? s_i[lane] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float oc = __shfl_xor_sync(0xffffffffu, bc, o);
+      const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(oc, oi, bc, bi, B.linvels, B.angvels, n_w)) {
+        bc = oc;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      SfwBest r;
+      r.valid = (bc >= 0.f) ? 1 : 0;
+      r.index = r.valid ? bi : 0u;
+      r.cost = r.valid ? bc : 0.f;
+      r.reserved0 = 0.f;
+      r.v = r.valid ? B.linvels[bi / n_w] : 0.0;
+      r.w = r.valid ? B.angvels[bi % n_w] : 0.0;
+      B.best[scene] = r;
+    }
+  }
+}
+
+// ================================================================================================
+cudaError_t sfw_crowd_prepare(size_t smem_bytes, int *blocks_per_sm) {
+  cudaError_t e = cudaFuncSetAttribute(sfw_score_crowd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e != cudaSuccess)
+    return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, sfw_score_crowd, kCrowdThreads, smem_bytes);
+}
+
+cudaError_t sfw_launch_crowd(const SfwBatchDev &B, unsigned int *work_counter, uint32_t grid, size_t smem_bytes,
+                             cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), stream);
+  if (e != cudaSuccess)
+    return e;
+  sfw_score_crowd<<<grid, kCrowdThreads, smem_bytes, stream>>>(B, work_counter);
+  e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return e;
+  sfw_argmin_kernel<<<B.n_scenes, 256, 0, stream>>>(B);
+  return cudaGetLastError();
+}

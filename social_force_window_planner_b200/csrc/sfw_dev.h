@@ -18,6 +18,8 @@
 #define SFW_MAX_PEDS_SMALL 64 /* thread-per-trajectory kernel: goal flags live in one 64-bit mask */
 #define SFW_FAR_AWAY 1.0e15f  /* padding pedestrian / obstacle: every force term underflows to exactly 0 */
 #define SFW_MAX_FOOTPRINT 64
+#define SFW_CROWD_THREADS 256  /* block-per-trajectory kernel (sfw_crowd.cu) */
+#define SFW_MAX_PEDS_CROWD 4096
 #define SFW_MAX_BLOCK_SMALL 512 /* launch bound of the thread-per-trajectory kernel (128 regs/thread) */
 
 struct SfwSceneDev {
@@ -52,6 +54,7 @@ struct SfwBatchDev {
   const float4 *pedGoal; // gx0, gx1, gy0, gy1
   const float4 *pedPar;  // goal_r^2 (0,1), desired_velocity (0,1)
   const float4 *pedPar2; // obs_scale (0,1), desired_velocity^2 (0,1)
+  const uint8_t *goal_bits; // [2 * pairs] 1 = pedestrian has a goal (same flags as SfwSceneDev::goal_mask)
   const float2 *obst; // obstacle points (scene frame) * log2(e)/sigma
   const double2 *footprint;
   const uint8_t *maps; // costmap slots: map_rows rows of map_pitch bytes each

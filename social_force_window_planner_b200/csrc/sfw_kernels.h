@@ -9,9 +9,15 @@
 // dynamic shared memory of sfw_score_small for a block of T threads
 size_t sfw_small_smem_bytes(uint32_t win_bytes, uint32_t P, uint32_t M, uint32_t F, uint32_t T);
 cudaError_t sfw_small_max_dynamic_smem(size_t *bytes);
+const char *sfw_small_kernel_name(uint32_t T); // variant a block of T threads dispatches to
 cudaError_t sfw_small_occupancy(uint32_t T, size_t smem_bytes, int *blocks_per_sm);
 cudaError_t sfw_launch_small(const SfwBatchDev &B, const CUtensorMap &tmap, uint32_t T,
                              size_t smem_bytes, cudaStream_t stream);
+// block-per-trajectory kernel for dense crowds (sfw_crowd.cu) + stand-alone arg-min
+size_t sfw_crowd_smem_bytes(uint32_t P, uint32_t M, uint32_t F, uint32_t S);
+cudaError_t sfw_crowd_prepare(size_t smem_bytes, int *blocks_per_sm);
+cudaError_t sfw_launch_crowd(const SfwBatchDev &B, unsigned int *work_counter, uint32_t grid, size_t smem_bytes,
+                             cudaStream_t stream);
 cudaError_t sfw_launch_points(const SfwBatchDev &B, uint32_t scene, uint32_t idx, uint32_t n_points,
                               double *out_xyz, cudaStream_t stream);
 #endif

@@ -156,3 +156,63 @@ def test_errors_are_reported_not_thrown(scorer):
     # the context stays usable
     costs, best = scorer.score(p, [sc], lin, ang)
     assert int(best[0]["valid"]) == 1
+
+
+# ---- dense crowds: block-per-trajectory kernel (sfw_crowd.cu) ---------------------------------------
+@pytest.mark.parametrize("n_peds", [65, 150, 151])
+def test_crowd_kernel_parity(scorer, n_peds):
+    wl = dataclasses.replace(S.WORKLOADS["C2"], n_v=6, n_w=6, steps=32, n_peds=n_peds, ped_r_max=6.0)
+    sc = S.make_scene(wl, 0)
+    p = wl.params()
+    lin, ang = wl.sample_arrays()
+    costs, best = scorer.score(p, [sc], lin, ang)
+    assert scorer.last_kernel == "sfw_score_crowd"
+    # with hundreds of agents most rollouts pass within the 5e-6 margin of SOME goal pop / sign flip;
+    # they are still compared (NEAR_RTOL) — only the "how many" sanity bound is relaxed
+    print(parity.compare(p, sc, lin, ang, costs[0], best[0], max_near_frac=1.0))
+
+
+def test_crowd_kernel_hazards_and_points(scorer):
+    """Costmap rejections, collisions and the recorded-point counts through the crowd kernel."""
+    import ctypes as C
+    import oracle_lib as ol
+    from social_force_window_planner_b200._abi import SceneArray
+    wl = dataclasses.replace(S.WORKLOADS["C0"], steps=40, n_peds=70, n_v=9, n_w=9)
+    sc = S.make_scene(wl, 3, hazards=True)
+    p = wl.params()
+    lin, ang = wl.sample_arrays()
+    costs, best = scorer.score(p, [sc], lin, ang)
+    assert scorer.last_kernel == "sfw_score_crowd"
+    st = parity.compare(p, sc, lin, ang, costs[0], best[0], max_near_frac=1.0)
+    assert 0 < st["valid"] < st["n"] - 1, st
+    sa = SceneArray([sc])
+    for idx in range(0, 81, 7):
+        if lin[idx // 9] == 0.0 and ang[idx % 9] == 0.0:
+            continue
+        pts, n = scorer.trajectory_points(0, idx)
+        n_o = C.c_uint32(0)
+        ol.oracle().sfw_oracle_score_trajectory(C.byref(p), None, sa.ptr(0), lin[idx // 9], 0.0, ang[idx % 9],
+                                                p.max_trans_acc, 0.0, p.max_rot_acc, None, 0, C.byref(n_o), None)
+        assert n == n_o.value, (idx, n, n_o.value)
+
+
+def test_crowd_batch_and_slab(scorer):
+    from social_force_window_planner_b200 import sharding
+    wl = dataclasses.replace(S.WORKLOADS["C2"], n_v=4, n_w=5, steps=16, n_peds=80, ped_r_max=5.0)
+    scs = [S.make_scene(wl, k) for k in range(3)]
+    p = wl.params()
+    lin, ang = wl.sample_arrays()
+    costs, best = scorer.score(p, scs, lin, ang)
+    for k in range(3):
+        c1, b1 = scorer.score(p, [scs[k]], lin, ang)
+        assert np.array_equal(c1[0], costs[k]) and b1[0] == best[k]
+    scorer.upload(p, [scs[1]], lin, ang)
+    recs = []
+    for r in range(2):
+        b, e = sharding.block_partition(len(lin), 2, r)
+        scorer.set_row_slab(b, e)
+        scorer.run()
+        c, bb = scorer.download()
+        assert np.array_equal(c[0][b * 5:e * 5], costs[1][b * 5:e * 5])
+        recs.append(bb[0])
+    assert sharding.merge_winners(np.array(recs)) == best[1]
