@@ -45,5 +45,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_LIB = os.path.join(HERE, "libsfw_planner_host.so")
+HOST_SRC = os.path.join(HERE, "host", "sfw_planner_host.cpp")
+
+
+def build_host(force: bool = False) -> str:
+    """libsfw_planner_host.so: the C++ mirror of the reference's SFWPlanner (host control flow + scene
+    packer) linked against libsfw_b200.so."""
+    build(force=False)
+    deps = [HOST_SRC, HOST_SRC.replace(".cpp", ".hpp"), os.path.join(HERE, "..", "include", "sfw_b200.h"), LIB]
+    if not force and os.path.exists(HOST_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_LIB) for d in deps):
+        return HOST_LIB
+    cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-Wextra", "-o", HOST_LIB,
+           HOST_SRC, "-L" + HERE, "-l:libsfw_b200.so", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building libsfw_planner_host.so")
+    return HOST_LIB
+
+
 if __name__ == "__main__":
+    build_host(force="--force" in sys.argv)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,476 @@
+// sfw_planner_host.cpp — see sfw_planner_host.hpp.  Host control flow of the reference's
+// SFWPlanner::findBestAction around ONE call into the CUDA scorer per tick.
+#include "sfw_planner_host.hpp"
+
+#include <cmath>
+#include <cstring>
+
+namespace social_force_window_planner {
+
+namespace {
+// reference sfw_planner.hpp:399-407 (all-float arithmetic)
+inline float normalizeAngle(float val, float min, float max) {
+  float norm = 0.0f;
+  if (val >= min)
+    norm = min + fmodf((val - min), (max - min));
+  else
+    norm = max - fmodf((min - val), (max - min));
+  return norm;
+}
+} // namespace
+
+SFWPlanner::SFWPlanner(const ControllerParams &params, const CostmapView *costmap,
+                       std::vector<Point2D> footprint_spec, int device)
+    : params_(params), costmap_(costmap), footprint_spec_(std::move(footprint_spec)), device_(device) {
+  // sample sets, reference sfw_planner.cpp:65-85
+  const int n_linvels = 4;
+  const double linvel_step = params_.max_vel_x_ / n_linvels;
+  for (int i = 0; i <= n_linvels; i++)
+    linvels_.push_back(i * linvel_step);
+  const int n_angvels = 4;
+  const double angvel_step = params_.max_vel_th_ / n_angvels;
+  angvels_.push_back(0.0);
+  for (int i = 1; i <= n_angvels; i++) {
+    angvels_.push_back(i * angvel_step);
+    angvels_.push_back(i * (-angvel_step));
+  }
+}
+
+SFWPlanner::~SFWPlanner() {
+  if (ctx_)
+    sfw_destroy(ctx_);
+}
+
+void SFWPlanner::setSampleSets(std::vector<double> linvels, std::vector<double> angvels) {
+  linvels_ = std::move(linvels);
+  angvels_ = std::move(angvels);
+}
+
+bool SFWPlanner::ensureContext() {
+  if (ctx_)
+    return true;
+  const int rc = sfw_create(&ctx_, device_, nullptr, nullptr);
+  if (rc != SFW_OK) {
+    error_ = sfw_last_error(nullptr);
+    ctx_ = nullptr;
+    return false;
+  }
+  return true;
+}
+
+uint64_t SFWPlanner::kernelLaunches() const { return ctx_ ? sfw_kernel_launches(ctx_) : 0; }
+
+// The scene packer: agents (sensor-interface layout) + live costmap + footprint -> SfwScene, then one
+// sfw_score.  agents[0] is the robot; all agents share agents[0]'s obstacle list (App. E-11).
+bool SFWPlanner::score(const float rx, const float ry, const float rt, const float rvx, const float rvy,
+                       const float rvt, double wpx, double wpy, const double *lin, uint32_t n_v,
+                       const double *ang, uint32_t n_w, std::vector<float> &costs, SfwBest &best) {
+  if (!ensureContext())
+    return false;
+  SfwParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.max_vel_x = params_.max_vel_x_;
+  p.max_trans_acc = params_.max_trans_acc_;
+  p.max_rot_acc = params_.max_rot_acc_;
+  p.sim_time = params_.sim_time_;
+  p.sim_granularity = params_.sim_granularity_;
+  p.robot_radius = params_.robot_radius_;
+  p.social_weight = params_.social_weight_;
+  p.costmap_weight = params_.costmap_weight_;
+  p.angle_weight = params_.angle_weight_;
+  p.distance_weight = params_.distance_weight_;
+  p.vel_weight = params_.vel_weight_;
+
+  SfwScene sc;
+  std::memset(&sc, 0, sizeof(sc));
+  sc.robot.x = rx;
+  sc.robot.y = ry;
+  sc.robot.theta = rt;
+  sc.robot.vx = rvx;
+  sc.robot.vy = rvy;
+  sc.robot.vtheta = rvt;
+  sc.robot.wpx = wpx;
+  sc.robot.wpy = wpy;
+  std::vector<SfwPed> peds;
+  std::vector<double> obs, fp;
+  if (!agents_.empty()) {
+    const Agent &r = agents_[0];
+    sc.robot.agent_x = r.position.x;
+    sc.robot.agent_y = r.position.y;
+    sc.robot.agent_vx = r.velocity.x;
+    sc.robot.agent_vy = r.velocity.y;
+    sc.robot.agent_radius = r.radius;
+    for (const Point2D &o : r.obstacles1) {
+      obs.push_back(o.x);
+      obs.push_back(o.y);
+    }
+    peds.resize(agents_.size() - 1);
+    for (size_t j = 1; j < agents_.size(); ++j) {
+      const Agent &a = agents_[j];
+      SfwPed &q = peds[j - 1];
+      std::memset(&q, 0, sizeof(q));
+      q.x = a.position.x;
+      q.y = a.position.y;
+      q.vx = a.velocity.x;
+      q.vy = a.velocity.y;
+      q.goal_x = a.goal_center.x;
+      q.goal_y = a.goal_center.y;
+      q.goal_radius = a.goal_radius;
+      q.desired_velocity = a.desiredVelocity;
+      q.radius = a.radius;
+      q.has_goal = a.has_goal ? 1 : 0;
+      q.group_id = a.groupId;
+      q.id = a.id;
+    }
+  } else { // no sensor data yet: the robot alone at its pose
+    sc.robot.agent_x = rx;
+    sc.robot.agent_y = ry;
+    sc.robot.agent_radius = params_.robot_radius_;
+  }
+  for (const Point2D &v : footprint_spec_) {
+    fp.push_back(v.x);
+    fp.push_back(v.y);
+  }
+  sc.costmap = costmap_->data;
+  sc.size_x = costmap_->size_x;
+  sc.size_y = costmap_->size_y;
+  sc.resolution = costmap_->resolution;
+  sc.origin_x = costmap_->origin_x;
+  sc.origin_y = costmap_->origin_y;
+  sc.peds = peds.empty() ? nullptr : peds.data();
+  sc.n_peds = (uint32_t)peds.size();
+  sc.obstacles_xy = obs.empty() ? nullptr : obs.data();
+  sc.n_obstacles = (uint32_t)(obs.size() / 2);
+  sc.footprint_xy = fp.empty() ? nullptr : fp.data();
+  sc.n_footprint = (uint32_t)(fp.size() / 2);
+
+  costs.assign((size_t)n_v * n_w, 0.0f);
+  const int rc = sfw_score(ctx_, &p, nullptr, &sc, lin, n_v, ang, n_w, costs.data(), &best);
+  if (rc != SFW_OK) {
+    error_ = sfw_last_error(ctx_);
+    staged_ = false;
+    return false;
+  }
+  staged_ = true;
+  return true;
+}
+
+std::vector<Point2D> SFWPlanner::trajectoryPoints(uint32_t sample_index) {
+  std::vector<Point2D> out;
+  if (!ctx_ || !staged_)
+    return out;
+  uint32_t n = 0;
+  std::vector<double> xyz(3 * 65536);
+  if (sfw_trajectory_points(ctx_, 0, sample_index, xyz.data(), 65536, &n) != SFW_OK)
+    return out;
+  out.resize(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    out[i].x = xyz[3 * i];
+    out[i].y = xyz[3 * i + 1];
+  }
+  return out;
+}
+
+// reference src/sfw_planner.cpp:117-469
+bool SFWPlanner::findBestAction(const Pose2D &global_pose, const Twist2D &global_vel, Twist2D &cmd_vel) {
+  goal_reached_ = false;
+  double vx, vy = 0.0, vt;
+  best_i_ = -1;
+
+  if (!running_) { // :131-142
+    cmd_vel.linear_x = 0.0;
+    cmd_vel.linear_y = 0.0;
+    cmd_vel.angular_z = 0.0;
+    return true;
+  }
+
+  // robot state narrowed to float exactly like the reference (:145-152)
+  float rx, ry, rt, rvx, rvy, rvt;
+  rx = global_pose.x;
+  ry = global_pose.y;
+  rt = global_pose.yaw;
+  rvx = global_vel.linear_x;
+  rvy = global_vel.linear_y;
+  rvt = global_vel.angular_z;
+
+  double dist_goal_sq = (rx - goal_x_) * (rx - goal_x_) + (ry - goal_y_) * (ry - goal_y_); // :167
+
+  if (dist_goal_sq < (params_.xy_goal_tolerance_ * params_.xy_goal_tolerance_)) { // :176-233
+    vx = 0.0;
+    if (fabs(goal_t_ - rt) < params_.yaw_goal_tolerance_) {
+      vt = 0.0;
+      running_ = false;
+      goal_reached_ = true;
+    } else {
+      float ang_diff = goal_t_ - rt;
+      ang_diff = normalizeAngle(ang_diff, -M_PI, M_PI);
+      if (ang_diff > 0.0)
+        vt = params_.min_in_place_vel_th_;
+      else
+        vt = -params_.min_in_place_vel_th_;
+      if (!params_.is_circular_) { // the rotation must be collision free: one scored trajectory
+        SfwBest b;
+        const double lin = vx, ang = vt;
+        const bool ok = score(rx, ry, rt, rvx, rvy, rvt, 0.0, 0.0, &lin, 1, &ang, 1, costs_, b);
+        if (!ok || costs_[0] < 0.0f) {
+          cmd_vel.linear_x = vx;
+          cmd_vel.linear_y = vy;
+          cmd_vel.angular_z = vt;
+          return false;
+        }
+      }
+    }
+    cmd_vel.linear_x = vx;
+    cmd_vel.linear_y = vy;
+    cmd_vel.angular_z = vt;
+    return true;
+  }
+
+  if (new_plan_) { // closest point of a fresh plan (:236-257)
+    new_plan_ = false;
+    double dist_sq;
+    double min_dist = 9999.0;
+    wp_index_ = 0;
+    for (int i = (int)global_plan_.size() - 1; i >= 0; i--) {
+      double wpx = global_plan_[i].x;
+      double wpy = global_plan_[i].y;
+      dist_sq = (rx - wpx) * (rx - wpx) + (ry - wpy) * (ry - wpy);
+      if (dist_sq < (params_.wp_tolerance_ * params_.wp_tolerance_)) {
+        wp_index_ = i;
+        break;
+      } else if (dist_sq < min_dist) {
+        min_dist = dist_sq;
+        wp_index_ = i;
+      }
+    }
+  }
+
+  double wpx = global_plan_[wp_index_].x; // :260-273
+  double wpy = global_plan_[wp_index_].y;
+  double dist_swp_sq = (rx - wpx) * (rx - wpx) + (ry - wpy) * (ry - wpy);
+  while (dist_swp_sq < (params_.wp_tolerance_ * params_.wp_tolerance_) &&
+         wp_index_ < (int)global_plan_.size() - 1) {
+    wp_index_++;
+    wpx = global_plan_[wp_index_].x;
+    wpy = global_plan_[wp_index_].y;
+    dist_swp_sq = (rx - wpx) * (rx - wpx) + (ry - wpy) * (ry - wpy);
+  }
+
+  double dx = (wpx - rx) * cos(rt) + (wpy - ry) * sin(rt); // :276-278
+  double dy = -(wpx - rx) * sin(rt) + (wpy - ry) * cos(rt);
+  double dt = atan2(dy, dx);
+
+  double dist_thres = 1.5; // approach branch (:282-334)
+  if (dist_goal_sq < (dist_thres * dist_thres)) {
+    vx = params_.min_vel_x_ + (params_.max_vel_x_ - params_.min_vel_x_) * (sqrt(dist_goal_sq) / dist_thres);
+    vy = 0.0;
+    vt = params_.min_vel_th_ + (params_.max_vel_th_ - params_.min_vel_th_) * fabs(dt) / M_PI;
+    if (dt < 0.0)
+      vt *= -1;
+    SfwBest b;
+    const double lin = vx, ang = vt;
+    if (score(rx, ry, rt, rvx, rvy, rvt, wpx, wpy, &lin, 1, &ang, 1, costs_, b) && costs_[0] >= 0.0f) {
+      cmd_vel.linear_x = vx;
+      cmd_vel.linear_y = vy;
+      cmd_vel.angular_z = vt;
+      markers_.assign(1, SampleMarker{vx, vt, costs_[0]});
+      best_i_ = 0;
+      return true;
+    }
+  }
+
+  // the (v, w) grid (:338-417): ONE launch; the arg-min with the reference's tie-breaks comes back
+  SfwBest best;
+  if (!score(rx, ry, rt, rvx, rvy, rvt, wpx, wpy, linvels_.data(), (uint32_t)linvels_.size(), angvels_.data(),
+             (uint32_t)angvels_.size(), costs_, best)) {
+    cmd_vel.linear_x = 0.0;
+    cmd_vel.linear_y = 0.0;
+    cmd_vel.angular_z = 0.0;
+    return false;
+  }
+  markers_.resize(costs_.size());
+  for (size_t i = 0; i < costs_.size(); ++i)
+    markers_[i] = SampleMarker{linvels_[i / angvels_.size()], angvels_[i % angvels_.size()], costs_[i]};
+
+  if (best.valid) { // :426-454
+    best_i_ = (int)best.index;
+    cmd_vel.linear_x = best.v;
+    cmd_vel.linear_y = 0.0;
+    cmd_vel.angular_z = best.w;
+    return true;
+  }
+  cmd_vel.linear_x = 0.0; // :456-468
+  cmd_vel.linear_y = 0.0;
+  cmd_vel.angular_z = 0.0;
+  return false;
+}
+
+// reference src/sfw_planner.cpp:853-892
+bool SFWPlanner::updatePlan(const std::vector<Pose2D> &new_plan) {
+  goal_reached_ = false;
+  global_plan_ = new_plan;
+  if (global_plan_.size() == 0) {
+    running_ = false;
+    wp_index_ = -1;
+    return true;
+  }
+  wp_index_ = 0;
+  running_ = true;
+  new_plan_ = true;
+  const Pose2D &goal_pose = global_plan_[global_plan_.size() - 1];
+  goal_x_ = goal_pose.x;
+  goal_y_ = goal_pose.y;
+  goal_t_ = goal_pose.yaw;
+  const Pose2D &start_pose = global_plan_[0];
+  start_x_ = start_pose.x;
+  start_y_ = start_pose.y;
+  start_t_ = start_pose.yaw;
+  return true;
+}
+
+// reference src/sfw_planner.cpp:894-901
+bool SFWPlanner::isGoalReached() {
+  if (goal_reached_) {
+    goal_reached_ = false; // we reset the flag
+    return true;
+  }
+  return goal_reached_;
+}
+
+} // namespace social_force_window_planner
+
+// ---------------------------------------------------------------------------------------------------
+// C wrapper so the tests (ctypes) can drive the class the way sfw_planner_node.cpp does.
+// ---------------------------------------------------------------------------------------------------
+using social_force_window_planner::Agent;
+using social_force_window_planner::ControllerParams;
+using social_force_window_planner::CostmapView;
+using social_force_window_planner::Point2D;
+using social_force_window_planner::Pose2D;
+using social_force_window_planner::SFWPlanner;
+using social_force_window_planner::Twist2D;
+
+struct sfwh_planner {
+  CostmapView view;
+  SFWPlanner *pl;
+};
+
+extern "C" {
+
+// ext: {min_vel_x, max_vel_th, min_vel_th, min_in_place_vel_th, yaw_goal_tolerance, xy_goal_tolerance,
+//       wp_tolerance, is_circular} (same order as oracle/ref_harness.cpp's sfw_ref_find_best_action)
+sfwh_planner *sfwh_create(const SfwParams *p, const double *ext, const SfwScene *scene, int device) {
+  ControllerParams cp;
+  cp.max_vel_x_ = p->max_vel_x;
+  cp.max_trans_acc_ = p->max_trans_acc;
+  cp.max_rot_acc_ = p->max_rot_acc;
+  cp.sim_time_ = p->sim_time;
+  cp.sim_granularity_ = p->sim_granularity;
+  cp.robot_radius_ = p->robot_radius;
+  cp.social_weight_ = p->social_weight;
+  cp.costmap_weight_ = p->costmap_weight;
+  cp.angle_weight_ = p->angle_weight;
+  cp.distance_weight_ = p->distance_weight;
+  cp.vel_weight_ = p->vel_weight;
+  if (ext) {
+    cp.min_vel_x_ = ext[0];
+    cp.max_vel_th_ = ext[1];
+    cp.min_vel_th_ = ext[2];
+    cp.min_in_place_vel_th_ = ext[3];
+    cp.yaw_goal_tolerance_ = ext[4];
+    cp.xy_goal_tolerance_ = ext[5];
+    cp.wp_tolerance_ = ext[6];
+    cp.is_circular_ = ext[7] != 0.0;
+  }
+  sfwh_planner *h = new sfwh_planner();
+  h->view.data = scene->costmap;
+  h->view.size_x = scene->size_x;
+  h->view.size_y = scene->size_y;
+  h->view.resolution = scene->resolution;
+  h->view.origin_x = scene->origin_x;
+  h->view.origin_y = scene->origin_y;
+  std::vector<Point2D> fp(scene->n_footprint);
+  for (uint32_t i = 0; i < scene->n_footprint; ++i) {
+    fp[i].x = scene->footprint_xy[2 * i];
+    fp[i].y = scene->footprint_xy[2 * i + 1];
+  }
+  h->pl = new SFWPlanner(cp, &h->view, fp, device);
+  // agents exactly as the sensor interface would hold them for this scene
+  std::vector<Agent> ag(scene->n_peds + 1);
+  std::vector<Point2D> obs(scene->n_obstacles);
+  for (uint32_t i = 0; i < scene->n_obstacles; ++i) {
+    obs[i].x = scene->obstacles_xy[2 * i];
+    obs[i].y = scene->obstacles_xy[2 * i + 1];
+  }
+  ag[0].id = -1;
+  ag[0].position = {scene->robot.agent_x, scene->robot.agent_y};
+  ag[0].velocity = {scene->robot.agent_vx, scene->robot.agent_vy};
+  ag[0].radius = scene->robot.agent_radius;
+  ag[0].obstacles1 = obs;
+  for (uint32_t j = 0; j < scene->n_peds; ++j) {
+    const SfwPed &q = scene->peds[j];
+    Agent &a = ag[j + 1];
+    a.id = q.id;
+    a.groupId = q.group_id;
+    a.position = {q.x, q.y};
+    a.velocity = {q.vx, q.vy};
+    a.radius = q.radius;
+    a.desiredVelocity = q.desired_velocity;
+    a.has_goal = q.has_goal != 0;
+    a.goal_center = {q.goal_x, q.goal_y};
+    a.goal_radius = q.goal_radius;
+    a.obstacles1 = obs;
+  }
+  h->pl->setAgents(std::move(ag));
+  return h;
+}
+
+void sfwh_destroy(sfwh_planner *h) {
+  if (!h)
+    return;
+  delete h->pl;
+  delete h;
+}
+
+void sfwh_set_samples(sfwh_planner *h, const double *lin, uint32_t n_v, const double *ang, uint32_t n_w) {
+  h->pl->setSampleSets(std::vector<double>(lin, lin + n_v), std::vector<double>(ang, ang + n_w));
+}
+
+void sfwh_get_samples(sfwh_planner *h, double *lin5, double *ang9) {
+  for (size_t i = 0; i < h->pl->linvels().size() && i < 5; ++i)
+    lin5[i] = h->pl->linvels()[i];
+  for (size_t i = 0; i < h->pl->angvels().size() && i < 9; ++i)
+    ang9[i] = h->pl->angvels()[i];
+}
+
+void sfwh_update_plan(sfwh_planner *h, const double *plan_xyt, uint32_t n) {
+  std::vector<Pose2D> plan(n);
+  for (uint32_t i = 0; i < n; ++i)
+    plan[i] = Pose2D{plan_xyt[3 * i], plan_xyt[3 * i + 1], plan_xyt[3 * i + 2]};
+  h->pl->updatePlan(plan);
+}
+
+// returns findBestAction's bool; cmd = {linear.x, linear.y, angular.z}
+int sfwh_find_best_action(sfwh_planner *h, const double *pose_xyt, const double *vel_xyt, double *cmd,
+                          int *wp_index, int *running, int *best_index, uint64_t *launches) {
+  Twist2D out;
+  const bool ok = h->pl->findBestAction(Pose2D{pose_xyt[0], pose_xyt[1], pose_xyt[2]},
+                                        Twist2D{vel_xyt[0], vel_xyt[1], vel_xyt[2]}, out);
+  cmd[0] = out.linear_x;
+  cmd[1] = out.linear_y;
+  cmd[2] = out.angular_z;
+  if (wp_index)
+    *wp_index = h->pl->wpIndex();
+  if (running)
+    *running = h->pl->running() ? 1 : 0;
+  if (best_index)
+    *best_index = h->pl->bestIndex();
+  if (launches)
+    *launches = h->pl->kernelLaunches();
+  return ok ? 1 : 0;
+}
+
+int sfwh_is_goal_reached(sfwh_planner *h) { return h->pl->isGoalReached() ? 1 : 0; }
+const char *sfwh_last_error(sfwh_planner *h) { return h->pl->lastError().c_str(); }
+
+} // extern "C"
