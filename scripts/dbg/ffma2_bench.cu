@@ -21,6 +21,9 @@ template <int MODE> __global__ void k(float *out, int iters, float a, float b) {
   asm("mov.b64 %0, {%1, %1};" : "=l"(pa) : "f"(a));
   asm("mov.b64 %0, {%1, %1};" : "=l"(pb) : "f"(b));
   u64 p[8];
+  unsigned xr[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) xr[i] = threadIdx.x + i;
 #pragma unroll
   for (int i = 0; i < 8; ++i) asm("mov.b64 %0, {%1, %2};" : "=l"(p[i]) : "f"(acc[2 * i]), "f"(acc[2 * i + 1]));
   for (int it = 0; it < iters; ++it) {
@@ -36,6 +39,50 @@ template <int MODE> __global__ void k(float *out, int iters, float a, float b) {
         float y;
         asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(acc[i]));
         acc[i] = y;
+      }
+    } else if (MODE == 4) {  // 8 FFMA2 + 8 scalar FFMA, independent chains: does scalar work ride for free?
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        p[i] = fma2(p[i], pa, pb);
+        acc[i] = fma1(acc[i], a, b);
+      }
+    } else if (MODE == 5) {  // 8 FFMA2 + 16 scalar FFMA
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        p[i] = fma2(p[i], pa, pb);
+        acc[2 * i] = fma1(acc[2 * i], a, b);
+        acc[2 * i + 1] = fma1(acc[2 * i + 1], a, b);
+      }
+    } else if (MODE == 6) {  // 8 FFMA2 + 4 MUFU
+#pragma unroll
+      for (int i = 0; i < 8; ++i) p[i] = fma2(p[i], pa, pb);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float y;
+        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(acc[i]));
+        acc[i] = y;
+      }
+    } else if (MODE == 7) {  // 8 FFMA2 + 8 integer LOP3/IADD (ALU pipe)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        p[i] = fma2(p[i], pa, pb);
+        unsigned u = __float_as_uint(acc[i]);
+        asm volatile("xor.b32 %0, %0, %1;" : "+r"(u) : "r"(it));
+        acc[i] = __uint_as_float(u);
+      }
+    } else if (MODE >= 8 && MODE <= 12) {
+      // 8: 16 FFMA + 8 XOR   9: 8 FFMA2 + 4 XOR   10: 8 FFMA2 + 16 XOR   11: 16 XOR   12: 16 FFMA + 16 XOR
+      constexpr int NX = (MODE == 8) ? 8 : (MODE == 9) ? 4 : 16;
+      if (MODE == 8 || MODE == 12) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fma1(acc[i], a, b);
+      } else if (MODE != 11) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p[i] = fma2(p[i], pa, pb);
+      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        asm volatile("xor.b32 %0, %0, %1;" : "+r"(xr[i]) : "r"(it));
       }
     } else if (MODE == 3) {  // mix: 1 MUFU per 4 FFMA2
 #pragma unroll
@@ -57,6 +104,8 @@ template <int MODE> __global__ void k(float *out, int iters, float a, float b) {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p[i]));
     s += lo + hi;
   }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += (float)xr[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 template <int MODE> void run(const char *name, double ops_per_iter_per_thread) {
@@ -82,5 +131,14 @@ int main() {
   run<1>("FFMA2 (8 per iter, 16 fma)", 16);
   run<2>("MUFU.EX2 (8 per iter)", 8);
   run<3>("8 FFMA2 + 2 MUFU", 18);
+  run<4>("8 FFMA2 + 8 FFMA", 24);
+  run<5>("8 FFMA2 + 16 FFMA", 32);
+  run<6>("8 FFMA2 + 4 MUFU", 20);
+  run<7>("8 FFMA2 + 8 XOR", 24);
+  run<8>("16 FFMA + 8 XOR", 24);
+  run<9>("8 FFMA2 + 4 XOR", 20);
+  run<10>("8 FFMA2 + 16 XOR", 32);
+  run<11>("16 XOR", 16);
+  run<12>("16 FFMA + 16 XOR", 32);
   return 0;
 }

@@ -34,7 +34,7 @@ struct Arena {
 
 struct Plan {
   // shape key
-  uint32_t n_scenes = 0, samples = 0, maxP = 0, maxM = 0, maxF = 0, win_bytes = 0;
+  uint32_t n_scenes = 0, samples = 0, maxP = 0, maxM = 0, maxF = 0, win_wp = 0, win_h = 0;
   // result
   uint32_t T = 0, tiles = 0;
   size_t smem = 0;
@@ -171,10 +171,10 @@ const SfwSfmParams kDefaultSfm = {2.0, 10.0, 0.2, 2.1, 3.0, 2.0, 1.0, 2.0, 0.35,
 // SM under the shared-memory and register limits, then shrink the block so a single-wave launch
 // is spread evenly over all SMs.
 int make_plan(sfw_ctx *c, uint32_t n_scenes, uint32_t samples, uint32_t P, uint32_t M, uint32_t F,
-              uint32_t win_bytes, int steps) {
+              uint32_t win_wp, uint32_t win_h, int steps) {
   Plan &pl = c->plan;
   if (pl.valid && pl.n_scenes == n_scenes && pl.samples == samples && pl.maxP == P && pl.maxM == M &&
-      pl.maxF == F && pl.win_bytes == win_bytes && pl.steps == steps)
+      pl.maxF == F && pl.win_wp == win_wp && pl.win_h == win_h && pl.steps == steps)
     return SFW_OK;
   uint32_t bestT = 0, bestK = 0;
   size_t max_dyn = 0;
@@ -183,7 +183,7 @@ int make_plan(sfw_ctx *c, uint32_t n_scenes, uint32_t samples, uint32_t P, uint3
   // (and its 64-bit goal mask stops fitting) beyond SFW_MAX_PEDS_SMALL.  Denser crowds go to the
   // block-per-trajectory kernel.
   bool try_small = P <= SFW_MAX_PEDS_SMALL;
-  if (try_small && sfw_small_smem_bytes(win_bytes, P, M, F, 128) > max_dyn)
+  if (try_small && sfw_small_smem_bytes(win_wp, win_h, P, M, F, 128) > max_dyn)
     try_small = false; // fewer than 4 warps per SM would fit
   if (!try_small) {
     const size_t smem = sfw_crowd_smem_bytes(P, M, F, (uint32_t)steps);
@@ -201,7 +201,8 @@ int make_plan(sfw_ctx *c, uint32_t n_scenes, uint32_t samples, uint32_t P, uint3
     pl.maxP = P;
     pl.maxM = M;
     pl.maxF = F;
-    pl.win_bytes = win_bytes;
+    pl.win_wp = win_wp;
+    pl.win_h = win_h;
     pl.steps = steps;
     pl.crowd = true;
     pl.grid = (uint32_t)std::min<uint64_t>(total, (uint64_t)c->sm_count * k);
@@ -214,7 +215,7 @@ int make_plan(sfw_ctx *c, uint32_t n_scenes, uint32_t samples, uint32_t P, uint3
   pl.crowd = false;
   pl.steps = steps;
   for (uint32_t T = SFW_MAX_BLOCK_SMALL; T >= 32; T -= 32) {
-    size_t smem = sfw_small_smem_bytes(win_bytes, P, M, F, T);
+    size_t smem = sfw_small_smem_bytes(win_wp, win_h, P, M, F, T);
     if (smem > max_dyn)
       continue;
     int k = 0;
@@ -248,10 +249,11 @@ int make_plan(sfw_ctx *c, uint32_t n_scenes, uint32_t samples, uint32_t P, uint3
   pl.maxP = P;
   pl.maxM = M;
   pl.maxF = F;
-  pl.win_bytes = win_bytes;
+  pl.win_wp = win_wp;
+  pl.win_h = win_h;
   pl.T = T;
   pl.tiles = (samples + T - 1) / T;
-  pl.smem = sfw_small_smem_bytes(win_bytes, P, M, F, T);
+  pl.smem = sfw_small_smem_bytes(win_wp, win_h, P, M, F, T);
   pl.valid = true;
   return SFW_OK;
 }
@@ -557,6 +559,13 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     d.fp_off = pF;
     d.map_off = slot * s;
     d.goal_mask = 0;
+    {
+      double circ = 0.0;
+      for (uint32_t k = 0; k < sc.n_footprint; ++k)
+        circ = std::max(circ, std::hypot(sc.footprint_xy[2 * k], sc.footprint_xy[2 * k + 1]));
+      const double rc = std::floor(circ / sc.resolution) + 2.0;
+      d.fp_rc = (sc.n_footprint >= 3 && rc < 64.0) ? (uint32_t)rc : 0u;
+    }
     // Pedestrian pair (2k, 2k+1): one float4 per quantity = (q0, q1) x (x, y).  An odd crowd is padded
     // with an agent SFW_FAR_AWAY from everything: all its pair/obstacle terms underflow to exactly 0.
     for (uint32_t k = 0; k < n_pairs; ++k) {
@@ -616,7 +625,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
 
   // ---- outputs -------------------------------------------------------------------------------
   const uint32_t samples = n_v * n_w;
-  rc = make_plan(c, n_scenes, samples, maxP, maxM, maxF, win_wp * win_h, num_steps);
+  rc = make_plan(c, n_scenes, samples, maxP, maxM, maxF, win_wp, win_h, num_steps);
   if (rc != SFW_OK)
     return rc;
   const uint32_t max_tiles = (samples + 31) / 32; // any slab / block size fits
@@ -747,7 +756,7 @@ int sfw_run(sfw_ctx *c) {
     Plan saved = c->plan;
     c->plan.valid = false;
     int rc = make_plan(c, B.n_scenes, std::max(samples, 1u), saved.maxP, saved.maxM, saved.maxF,
-                       saved.win_bytes, saved.steps);
+                       saved.win_wp, saved.win_h, saved.steps);
     if (rc != SFW_OK)
       return rc;
     B.tiles_per_scene = c->plan.tiles;

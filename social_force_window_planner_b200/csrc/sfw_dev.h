@@ -38,6 +38,9 @@ struct SfwSceneDev {
   uint32_t n_pairs;                  // ceil(n_peds / 2); an odd crowd is padded with a far-away agent
   uint64_t map_off; // byte offset of this scene's costmap slot
   uint64_t goal_mask; // bit j: pedestrian j has a goal (sfm::Agent::goals non-empty)
+  // every cell the footprint can touch lies within fp_rc cells (Chebyshev) of the robot's own cell:
+  // floor(circumscribed radius / resolution) + 2; 0 switches the free-space shortcut off
+  uint32_t fp_rc, pad1;
 };
 
 struct SfwBlockBest {

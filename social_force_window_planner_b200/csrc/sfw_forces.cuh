@@ -335,6 +335,8 @@ struct MapView {
   uint32_t sx, sy, pitch;
   int32_t wx0, wy0;
   uint32_t wwp, wh;     // window pitch / rows
+  const uint32_t *free_bits; // [wh][fw32] bit = whole (2 fp_rc + 1)^2 neighbourhood is in the map and free (or nullptr)
+  uint32_t fw32;
 };
 
 __device__ __forceinline__ uint32_t cell_cost(const MapView &m, int cx, int cy) {
@@ -425,6 +427,14 @@ __device__ __forceinline__ int footprint_cost(const MapView &m, const double2 *_
   if (F < 3) {
     const int c = (int)cell_cost(m, cx, cy);
     return (c >= 253) ? -1 : c;
+  }
+  // Free-space shortcut (exact): every vertex cell and every Bresenham cell between two of them lies in
+  // the square of +-fp_rc cells around the centre cell.  If that whole square is inside the map and
+  // holds only cost 0, every vertex maps and the maximum over any subset of its cells is 0.
+  if (m.free_bits) {
+    const uint32_t lx = (uint32_t)(cx - m.wx0), ly = (uint32_t)(cy - m.wy0);
+    if (lx < m.wwp && ly < m.wh && ((m.free_bits[ly * m.fw32 + (lx >> 5)] >> (lx & 31u)) & 1u))
+      return 0;
   }
   int worst = 0;
   int fx0 = 0, fy0 = 0, px = 0, py = 0;

@@ -83,6 +83,12 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   float *s_redc = reinterpret_cast<float *>(smem_raw + off);
   uint32_t *s_redi = reinterpret_cast<uint32_t *>(smem_raw + off + 32u * 4u);
   off += 64u * 4u;
+  // free-space bit maps over the window (row pass, then the final one)
+  const uint32_t fw32 = (B.win_wp + 31u) >> 5;
+  uint32_t *s_rowfree = reinterpret_cast<uint32_t *>(smem_raw + off);
+  off += ((win_bytes ? B.win_h * fw32 * 4u : 0u) + 15u) & ~15u;
+  uint32_t *s_free = reinterpret_cast<uint32_t *>(smem_raw + off);
+  off += ((win_bytes ? B.win_h * fw32 * 4u : 0u) + 15u) & ~15u;
   float4 *s_pos = reinterpret_cast<float4 *>(smem_raw + off);
   off += P2 * T * 16u;
   float4 *s_vel = reinterpret_cast<float4 *>(smem_raw + off);
@@ -116,6 +122,42 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   __syncthreads(); // barrier init visible to the waiters
   mbar_wait(s_bar, 0);
 
+  // ---- free-space map of the window: bit (lx, ly) set <=> all cells within fp_rc of it are inside the
+  // map and cost 0.  Separable: a row pass (ballot per 32 cells), then an AND over 2 fp_rc + 1 rows.
+  const uint32_t fp_rc = scp->fp_rc;
+  const bool use_free = win_bytes != 0u && fp_rc != 0u && F >= 3u;
+  if (use_free) {
+    const int r = (int)fp_rc, ww = (int)B.win_wp, wh = (int)B.win_h;
+    const int gx0 = scp->win_x0, gy0 = scp->win_y0, sx = (int)scp->size_x, sy = (int)scp->size_y;
+    const uint32_t n_words = B.win_h * fw32;
+    for (uint32_t wd = tid >> 5; wd < n_words; wd += T >> 5) { // T is a multiple of 32
+      const int ly = (int)(wd / fw32), lx = (int)((wd % fw32) * 32u + (tid & 31u));
+      bool ok = lx - r >= 0 && lx + r < ww && gx0 + lx - r >= 0 && gx0 + lx + r < sx && gy0 + ly >= 0 && gy0 + ly < sy;
+      if (ok) {
+        const uint8_t *row = s_win + ly * ww + lx;
+        uint32_t acc = 0;
+        for (int d = -r; d <= r; ++d)
+          acc |= row[d];
+        ok = acc == 0u;
+      }
+      const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+      if ((tid & 31u) == 0)
+        s_rowfree[wd] = bits;
+    }
+    __syncthreads();
+    for (uint32_t wd = tid; wd < n_words; wd += T) {
+      const int ly = (int)(wd / fw32);
+      uint32_t bits = 0u;
+      if (ly - r >= 0 && ly + r < wh) {
+        bits = 0xffffffffu;
+        for (int d = -r; d <= r; ++d)
+          bits &= s_rowfree[wd + d * (int)fw32];
+      }
+      s_free[wd] = bits;
+    }
+    __syncthreads();
+  }
+
   MapView mv;
   mv.win = win_bytes ? s_win : nullptr;
   mv.glob = B.maps + scp->map_off;
@@ -130,6 +172,8 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   mv.wy0 = scp->win_y0;
   mv.wwp = win_bytes ? B.win_wp : 0u;
   mv.wh = win_bytes ? B.win_h : 0u;
+  mv.free_bits = use_free ? s_free : nullptr;
+  mv.fw32 = fw32;
 
   const SfmConst K = {B.lambda, B.c_d, B.gamma * B.gamma, B.c_np, B.c_n, B.k_soc};
 
@@ -490,7 +534,8 @@ extern "C" __global__ void sfw_points_kernel(const __grid_constant__ SfwBatchDev
 // ================================================================================================
 // launch wrappers (called from sfw_abi.cu)
 // ================================================================================================
-size_t sfw_small_smem_bytes(uint32_t win_bytes, uint32_t P, uint32_t M, uint32_t F, uint32_t T) {
+size_t sfw_small_smem_bytes(uint32_t win_wp, uint32_t win_h, uint32_t P, uint32_t M, uint32_t F, uint32_t T) {
+  const uint32_t win_bytes = win_wp * win_h;
   const size_t P2 = (P + 1u) / 2u, Mp = (M + 1u) & ~1u;
   size_t off = (win_bytes + 127u) & ~127u;
   off += 5u * P2 * 16u;
@@ -498,6 +543,7 @@ size_t sfw_small_smem_bytes(uint32_t win_bytes, uint32_t P, uint32_t M, uint32_t
   off += (size_t)F * 16u;
   off += 16u;
   off += 64u * 4u;
+  off += 2u * ((win_bytes ? (size_t)win_h * ((win_wp + 31u) / 32u) * 4u : 0u) + 15u & ~(size_t)15u);
   off += 3u * P2 * T * 16u;
   return off;
 }
