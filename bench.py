@@ -359,7 +359,13 @@ def main():
         ck = clocks.summary()
         f_sm = (ck["sm_mhz"] or 1965.0) * 1e6
         evals_per_s = (pair + obst) * wl.samples / (k_ms * 1e-3)
-        mufu_per_s = (6 * pair + 3 * obst) * wl.samples / (k_ms * 1e-3)
+        # MUFU operations the kernels actually execute per trajectory: every unordered
+        # pedestrian pair and every robot-pedestrian pair once per step (2 rsqrt + 2 ex2, + 1 sqrt for the
+        # social-work magnitude of the robot pairs), 2 per obstacle term (rsqrt, ex2), 2 rsqrt per
+        # pedestrian update (goal direction, speed cap), one extra robot-pedestrian pass after the last step.
+        P_, M_, S_ = wl.n_peds, wl.n_obstacles, wl.steps
+        mufu_exec = S_ * (4 * (P_ * (P_ - 1) // 2 + P_) + P_ + 2 * (P_ + 1) * M_ + 2 * P_) + 5 * P_
+        mufu_per_s = mufu_exec * wl.samples / (k_ms * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -374,10 +380,12 @@ def main():
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo_bytes),
                          "note": "path is FP32/MUFU-issue bound (about 1e5 flop per algorithmic byte); see issue"},
-            "issue": {"interaction_evals_per_s": evals_per_s, "nominal_mufu_per_s": mufu_per_s,
-                      "mufu_peak_per_s": 148 * 16 * f_sm, "mufu_frac": mufu_per_s / (148 * 16 * f_sm),
-                      "model": "reference work: S*[N(N-1)+(N-1)] pair + S*N*M obstacle evals per trajectory, "
-                               "6 / 3 MUFU each (SURVEY.md 8d)"},
+            "issue": {"reference_interaction_evals_per_s": evals_per_s,
+                      "mufu_executed_per_s": mufu_per_s, "mufu_peak_per_s": 148 * 16 * f_sm,
+                      "mufu_frac": mufu_per_s / (148 * 16 * f_sm),
+                      "model": "reference work (SURVEY.md 8d): S*[N(N-1)+(N-1)] pair + S*N*M obstacle evaluations per "
+                               "trajectory; MUFU count: what the kernel executes (each unordered pair once, 4 MUFU; "
+                               "obstacle term 2 MUFU) against 16 MUFU/clk/SM at the sampled SM clock"},
             "clocks": ck,
             "winner": {"valid": int(best_dev[0]["valid"]), "index": int(best_dev[0]["index"]),
                        "v": float(best_dev[0]["v"]), "w": float(best_dev[0]["w"]), "cost": float(best_dev[0]["cost"])},

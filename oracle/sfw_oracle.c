@@ -327,7 +327,7 @@ static void desired_force(const SfwSfmParams *P, OAgent *a, double *goal_margin)
 }
 
 /* App. B-4 (only for groupId >= 0 with >= 2 members) */
-static void group_force(const SfwSfmParams *P, OAgent *ag, int n, int idx) {
+static void group_force(const SfwSfmParams *P, OAgent *ag, int n, int idx, double *contact_margin) {
   OAgent *a = &ag[idx];
   a->fgx = 0.0;
   a->fgy = 0.0;
@@ -373,6 +373,11 @@ static void group_force(const SfwSfmParams *P, OAgent *ag, int n, int idx) {
     if (i == idx || ag[i].group != a->group)
       continue;
     double dx = a->px - ag[i].px, dy = a->py - ag[i].py;
+    if (contact_margin) { /* the repulsion term switches on at contact: a discontinuity of the model */
+      double m = fabs(sqrt(dx * dx + dy * dy) - (a->radius + ag[i].radius));
+      if (m < *contact_margin)
+        *contact_margin = m;
+    }
     if (sqrt(dx * dx + dy * dy) < a->radius + ag[i].radius) {
       rpx += dx;
       rpy += dy;
@@ -404,7 +409,7 @@ static void compute_forces(const SfwSfmParams *P, OAgent *ag, int n, const doubl
       if (mg && mag > 1e-6 && fabs(th) < mg->theta)
         mg->theta = fabs(th);
     }
-    group_force(P, ag, n, i);
+    group_force(P, ag, n, i, mg ? &mg->collision : NULL);
     a->Fx = a->fdx + a->fsx + a->fox + a->fgx;
     a->Fy = a->fdy + a->fsy + a->foy + a->fgy;
   }

@@ -26,7 +26,8 @@ extern "C" {
  * float-vs-double rounding difference from a branch flip (goal pop, collision, sign(theta)). */
 typedef struct SfwOracleMargins {
   double goal;      /* min over steps/peds of | |goal - p| - goal_radius |  (metres) */
-  double collision; /* min over steps/peds of | |robot - ped| - robot_radius | (metres) */
+  double collision; /* min over steps/peds of | |robot - ped| - robot_radius | and, for grouped pedestrians,
+                     * of | |p_a - p_b| - (r_a + r_b) | (group repulsion switches on at contact) (metres) */
   double theta;     /* min over non-negligible pair evaluations of |theta| (radians) */
   double cell;      /* min distance (metres) of any rasterised world point to a cell boundary */
 } SfwOracleMargins;

@@ -398,16 +398,6 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     if (sc.n_footprint > SFW_MAX_FOOTPRINT)
       return fail(c, SFW_ERR_UNSUPPORTED, "scene %u: footprint with %u vertices > %d", s,
                   sc.n_footprint, SFW_MAX_FOOTPRINT);
-    for (uint32_t j = 0; j < sc.n_peds; ++j) {
-      if (sc.peds[j].group_id >= 0) {
-        for (uint32_t k = j + 1; k < sc.n_peds; ++k)
-          if (sc.peds[k].group_id == sc.peds[j].group_id)
-            return fail(c, SFW_ERR_UNSUPPORTED,
-                        "scene %u: pedestrian groups (group_id >= 0 shared by >= 2 agents) are not "
-                        "implemented by the kernels yet",
-                        s);
-      }
-    }
     maxP = std::max(maxP, sc.n_peds);
     maxM = std::max(maxM, sc.n_obstacles);
     maxF = std::max(maxF, sc.n_footprint);
@@ -416,6 +406,46 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     totP += (sc.n_peds + 1) / 2;         // pedestrians are stored as pairs
     totM += align_up(sc.n_obstacles, 2); // obstacle lists are padded to an even count
     totF += sc.n_footprint;
+  }
+
+  // ---- pedestrian groups: lightsfm only applies group forces to groups with >= 2 members ------
+  std::vector<uint32_t> grp_table;
+  std::vector<uint32_t> grp_off(n_scenes), grp_cnt(n_scenes);
+  {
+    std::vector<std::pair<int32_t, uint32_t>> tagged;
+    for (uint32_t s = 0; s < n_scenes; ++s) {
+      const SfwScene &sc = scenes[s];
+      tagged.clear();
+      for (uint32_t j = 0; j < sc.n_peds; ++j)
+        if (sc.peds[j].group_id >= 0)
+          tagged.emplace_back(sc.peds[j].group_id, j);
+      std::stable_sort(tagged.begin(), tagged.end(),
+                       [](const std::pair<int32_t, uint32_t> &a, const std::pair<int32_t, uint32_t> &b) { return a.first < b.first; });
+      std::vector<uint32_t> starts, members;
+      for (size_t i = 0; i < tagged.size();) {
+        size_t e = i;
+        while (e < tagged.size() && tagged[e].first == tagged[i].first)
+          ++e;
+        if (e - i >= 2) {
+          starts.push_back((uint32_t)(members.size() / 2));
+          for (size_t m = i; m < e; ++m) {
+            const float rad = (float)sc.peds[tagged[m].second].radius;
+            uint32_t bits;
+            memcpy(&bits, &rad, 4);
+            members.push_back(tagged[m].second);
+            members.push_back(bits);
+          }
+        }
+        i = e;
+      }
+      grp_off[s] = (uint32_t)grp_table.size();
+      grp_cnt[s] = (uint32_t)starts.size();
+      if (!starts.empty()) {
+        starts.push_back((uint32_t)(members.size() / 2));
+        grp_table.insert(grp_table.end(), starts.begin(), starts.end());
+        grp_table.insert(grp_table.end(), members.begin(), members.end());
+      }
+    }
   }
 
   // ---- rollout constants --------------------------------------------------------------------
@@ -495,6 +525,8 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   off = align_up(off + 8 * totM, kAlign);
   const size_t o_fp = off;
   off = align_up(off + 16 * totF, kAlign);
+  const size_t o_grp = off;
+  off = align_up(off + 4 * grp_table.size(), kAlign);
   const size_t o_lin = off;
   off = align_up(off + 8 * (size_t)n_v, kAlign);
   const size_t o_ang = off;
@@ -517,6 +549,8 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   uint8_t *hBits = h + o_gbits;
   float2 *hO = reinterpret_cast<float2 *>(h + o_obs);
   double2 *hF = reinterpret_cast<double2 *>(h + o_fp);
+  if (!grp_table.empty())
+    memcpy(h + o_grp, grp_table.data(), 4 * grp_table.size());
   memcpy(h + o_lin, linvels, 8 * (size_t)n_v);
   memcpy(h + o_ang, angvels, 8 * (size_t)n_w);
   uint32_t pP = 0, pM = 0, pF = 0;
@@ -559,6 +593,8 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     d.fp_off = pF;
     d.map_off = slot * s;
     d.goal_mask = 0;
+    d.n_groups = grp_cnt[s];
+    d.grp_off = grp_off[s];
     {
       double circ = 0.0;
       for (uint32_t k = 0; k < sc.n_footprint; ++k)
@@ -664,6 +700,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   B.goal_bits = dv + o_gbits;
   B.obst = reinterpret_cast<const float2 *>(dv + o_obs);
   B.footprint = reinterpret_cast<const double2 *>(dv + o_fp);
+  B.groups = reinterpret_cast<const uint32_t *>(dv + o_grp);
   B.maps = dv + o_maps;
   B.linvels = reinterpret_cast<const double *>(dv + o_lin);
   B.angvels = reinterpret_cast<const double *>(dv + o_ang);
@@ -704,6 +741,9 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   B.inv_tau = (float)(1.0 / sfm.relaxation_time);
   B.c_obs = (float)(log2e * inv_sigma);
   B.dtf = (float)dt;
+  B.k_gaze = (float)sfm.force_factor_group_gaze;
+  B.k_coh = (float)sfm.force_factor_group_coherence;
+  B.k_rep = (float)sfm.force_factor_group_repulsion;
   if (win_wp) {
     rc = make_tensor_map(c, B.maps, map_pitch, map_rows, n_scenes, win_wp, win_h);
     if (rc != SFW_OK)

@@ -115,6 +115,7 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
     const uint32_t idx = B.row_begin * n_w + (item - scene * per_scene);
     const SfwSceneDev *__restrict__ scp = B.scenes + scene;
     const uint32_t P2 = scp->n_pairs, M = scp->n_obst, F = scp->n_fp;
+    const uint32_t n_groups = scp->n_groups;
     const CrowdSmem sm = carve(smem_raw, P2, M, F, (uint32_t)S);
     const double v_s = B.linvels[idx / n_w], w_s = B.angvels[idx % n_w];
     const size_t out = (size_t)scene * B.n_v * n_w + idx;
@@ -267,6 +268,29 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
       const f2 RX = bc2(prx), RY = bc2(pry), RVX = bc2(rvxf), RVY = bc2(rvyf);
       f2 rfx2 = bc2(0.f), rfy2 = bc2(0.f), wp2 = bc2(0.f);
 
+      // -- phase 0: group forces (lightsfm computeGroupForce), one member per thread, into the warp's row --
+      if (n_groups) {
+        const uint32_t *gt = B.groups + scp->grp_off;
+        const uint32_t *mem0 = gt + n_groups + 1u;
+        const uint32_t n_members = gt[n_groups];
+        const float *Pf = reinterpret_cast<const float *>(sm.pos);
+        float *Ff = reinterpret_cast<float *>(myrow);
+        for (uint32_t q = tid; q < n_members; q += kCrowdThreads) {
+          uint32_t g = 0;
+          while (gt[g + 1u] <= q)
+            ++g;
+          const uint32_t s0 = gt[g], c = gt[g + 1u] - s0;
+          const uint32_t *mem = mem0 + 2u * s0;
+          float cx, cy, ddx, ddy, gfx, gfy;
+          group_centre(mem, c, Pf, 4u, cx, cy);
+          const uint32_t j = mem[2u * (q - s0)];
+          desired_direction(Pf, 4u, sm.goal, sm.par, j, sm.goalflag[j] != 0, ddx, ddy);
+          group_member_force(mem, c, q - s0, Pf, 4u, cx, cy, ddx, ddy, B.k_gaze, B.k_coh, B.k_rep, gfx, gfy);
+          Ff[(j >> 1) * 4u + (j & 1u)] += gfx;
+          Ff[(j >> 1) * 4u + 2u + (j & 1u)] += gfy;
+        }
+        __syncwarp();
+      }
       // -- phase 1: forces (sfw_planner.cpp:592) --
       for (uint32_t m = 0; m < owned; ++m) {
         const uint32_t a = tid + m * kCrowdThreads;

@@ -40,7 +40,11 @@ struct SfwSceneDev {
   uint64_t goal_mask; // bit j: pedestrian j has a goal (sfm::Agent::goals non-empty)
   // every cell the footprint can touch lies within fp_rc cells (Chebyshev) of the robot's own cell:
   // floor(circumscribed radius / resolution) + 2; 0 switches the free-space shortcut off
-  uint32_t fp_rc, pad1;
+  uint32_t fp_rc;
+  // pedestrian groups (lightsfm computeGroupForce): table at SfwBatchDev::groups + grp_off, laid out as
+  // start[0..n_groups] (member index of each group's first member), then 2 words per member:
+  // pedestrian index, radius (float bits).  Only groups with >= 2 members in the scene are listed.
+  uint32_t n_groups, grp_off, pad1;
 };
 
 struct SfwBlockBest {
@@ -59,6 +63,7 @@ struct SfwBatchDev {
   const float4 *pedPar2; // obs_scale (0,1), desired_velocity^2 (0,1)
   const uint8_t *goal_bits; // [2 * pairs] 1 = pedestrian has a goal (same flags as SfwSceneDev::goal_mask)
   const float2 *obst; // obstacle points (scene frame) * log2(e)/sigma
+  const uint32_t *groups; // per-scene group tables (SfwSceneDev::grp_off)
   const double2 *footprint;
   const uint8_t *maps; // costmap slots: map_rows rows of map_pitch bytes each
   const double *linvels;
@@ -91,6 +96,8 @@ struct SfwBatchDev {
   float inv_tau;    // 1 / relaxationTime
   float c_obs;      // log2(e) / sigma
   float dtf;        // (float)dt
+  float k_gaze, k_coh, k_rep; // forceFactorGroupGaze / Coherence / Repulsion
+  float pad2;
 };
 
 #endif

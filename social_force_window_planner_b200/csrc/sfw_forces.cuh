@@ -326,6 +326,89 @@ __device__ __forceinline__ void obstacle_sum1(const float2 *__restrict__ obs, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// lightsfm group forces (lightsfm computeGroupForce, reached through the
+// computeForces call at reference src/sfw_planner.cpp:592) for ONE member of one group, FP32.
+//   gaze:       k_gaze * (dd . rel) * dd  when the centre of mass of the OTHER members lies behind the
+//               desired direction dd (angle > 90 deg <=> dd . rel < 0; dd == 0 without a live goal -> none)
+//   coherence:  k_coh * (tanh(dist - (c-1)/2) + 1)/2 * (centre - p) = k_coh * sigmoid(2 x) * (centre - p)
+//   repulsion:  k_rep * sum over members closer than r_a + r_b of (p_a - p_b)
+// Positions are read through (pair k, half h): P[k * stride + h] = x, P[k * stride + 2 + h] = y with
+// `stride` floats between consecutive pairs (4 for a plain float4 array, 4*T for the per-thread columns
+// of the thread-per-trajectory kernel).  `mem` points at the group's member records (ped index, radius).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void group_member_force(const uint32_t *__restrict__ mem, uint32_t c, uint32_t self,
+                                                   const float *P, uint32_t stride, float cx, float cy,
+                                                   float ddx, float ddy, float k_gaze, float k_coh, float k_rep,
+                                                   float &fx, float &fy) {
+  const uint32_t j = mem[2u * self];
+  const float rad = __uint_as_float(mem[2u * self + 1u]);
+  const uint32_t k = j >> 1, h = j & 1u;
+  const float px = P[k * stride + h], py = P[k * stride + 2u + h];
+  const float fc = (float)c;
+  // gaze: centre of mass of the others = (c * centre - p) / (c - 1)
+  const float inv_cm1 = 1.0f / (fc - 1.0f);
+  const float relx = (fc * cx - px) * inv_cm1 - px, rely = (fc * cy - py) * inv_cm1 - py;
+  const float ep = fmaf(ddx, relx, ddy * rely);
+  const float gz = (ep < 0.0f) ? k_gaze * ep : 0.0f;
+  fx = gz * ddx;
+  fy = gz * ddy;
+  // coherence
+  const float rx = cx - px, ry = cy - py;
+  const float d2 = fmaf(rx, rx, ry * ry);
+  const float dist = d2 * rsqrt_approx(fmaxf(d2, 1e-30f));
+  const float x = dist - 0.5f * (fc - 1.0f);
+  const float soft = k_coh * rcp_approx(1.0f + ex2_approx(-2.885390081777927f * x)); // sigmoid(2x)
+  fx = fmaf(rx, soft, fx);
+  fy = fmaf(ry, soft, fy);
+  // repulsion
+  float rpx = 0.f, rpy = 0.f;
+  for (uint32_t m = 0; m < c; ++m) {
+    if (m == self)
+      continue;
+    const uint32_t j2 = mem[2u * m];
+    const float rr = rad + __uint_as_float(mem[2u * m + 1u]);
+    const uint32_t k2 = j2 >> 1, h2 = j2 & 1u;
+    const float dx = px - P[k2 * stride + h2], dy = py - P[k2 * stride + 2u + h2];
+    if (fmaf(dx, dx, dy * dy) < rr * rr) {
+      rpx += dx;
+      rpy += dy;
+    }
+  }
+  fx = fmaf(k_rep, rpx, fx);
+  fy = fmaf(k_rep, rpy, fy);
+}
+
+// centre of a group (mean of the member positions)
+__device__ __forceinline__ void group_centre(const uint32_t *__restrict__ mem, uint32_t c, const float *P,
+                                             uint32_t stride, float &cx, float &cy) {
+  float sx = 0.f, sy = 0.f;
+  for (uint32_t m = 0; m < c; ++m) {
+    const uint32_t j = mem[2u * m];
+    const uint32_t k = j >> 1, h = j & 1u;
+    sx += P[k * stride + h];
+    sy += P[k * stride + 2u + h];
+  }
+  const float inv = 1.0f / (float)c;
+  cx = sx * inv;
+  cy = sy * inv;
+}
+
+// desired direction of pedestrian j (computeDesiredForce's return value): unit vector to a live goal, else 0
+__device__ __forceinline__ void desired_direction(const float *P, uint32_t stride, const float4 *__restrict__ goal,
+                                                  const float4 *__restrict__ par, uint32_t j, bool has_goal,
+                                                  float &ddx, float &ddy) {
+  const uint32_t k = j >> 1, h = j & 1u;
+  const float *G = reinterpret_cast<const float *>(goal + k);
+  const float *R = reinterpret_cast<const float *>(par + k);
+  const float gx = G[h] - P[k * stride + h], gy = G[2u + h] - P[k * stride + 2u + h];
+  const float g2 = fmaf(gx, gx, gy * gy);
+  const bool on = has_goal && g2 > R[h];
+  const float rg = on ? rsqrt_approx(g2) : 0.0f;
+  ddx = gx * rg;
+  ddy = gy * rg;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Costmap access + footprint rasterisation (bit-faithful integer work)
 // ------------------------------------------------------------------------------------------------
 struct MapView {

@@ -57,6 +57,7 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   const uint32_t tile = blockIdx.x - scene * B.tiles_per_scene;
   const SfwSceneDev *__restrict__ scp = B.scenes + scene;
   const uint32_t P2 = scp->n_pairs, M = scp->n_obst, F = scp->n_fp;
+  const uint32_t n_groups = scp->n_groups;
 
   // ---- shared memory carve-up -------------------------------------------------------------
   // [window][pos P2][vel P2][goal P2][par P2][par2 P2][obst M][footprint F][mbar][tile best]
@@ -253,6 +254,28 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
         bool hit = false;
         const f2 RX = bc2(prx), RY = bc2(pry), RVX = bc2(rvxf), RVY = bc2(rvyf);
         const f2 DT = bc2(dtf);
+        // group forces of computeForces (lightsfm computeGroupForce): added to the (zeroed) accumulators
+        if (n_groups) {
+          const uint32_t *gt = B.groups + scp->grp_off;
+          const uint32_t *mem0 = gt + n_groups + 1u;
+          const float *Pf = reinterpret_cast<const float *>(pos);
+          float *Ff = reinterpret_cast<float *>(frc);
+          const uint32_t st = 4u * T;
+          for (uint32_t g = 0; g < n_groups; ++g) {
+            const uint32_t s0 = gt[g], c = gt[g + 1u] - s0;
+            const uint32_t *mem = mem0 + 2u * s0;
+            float cx, cy;
+            group_centre(mem, c, Pf, st, cx, cy);
+            for (uint32_t m = 0; m < c; ++m) {
+              const uint32_t j = mem[2u * m];
+              float ddx, ddy, gfx, gfy;
+              desired_direction(Pf, st, s_goal, s_par, j, (goalmask >> j) & 1ull, ddx, ddy);
+              group_member_force(mem, c, m, Pf, st, cx, cy, ddx, ddy, B.k_gaze, B.k_coh, B.k_rep, gfx, gfy);
+              Ff[(j >> 1) * st + (j & 1u)] += gfx;
+              Ff[(j >> 1) * st + 2u + (j & 1u)] += gfy;
+            }
+          }
+        }
         for (uint32_t k = 0; k < P2; ++k) {
           const float4 pa = pos[k * T], va = vel[k * T], fa4 = frc[k * T];
           const f2 AX = mk2(pa.x, pa.y), AY = mk2(pa.z, pa.w);

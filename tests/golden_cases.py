@@ -32,6 +32,29 @@ def _yaml_like(p):
     p.vel_weight = 0.8
 
 
+def _grouped(wl, seed, groups, spread=0.45, **scene_kw):
+    """Scene whose pedestrians carry people-message group tags (reference src/sensor_interface.cpp:449):
+    ``groups`` = {group_id: [pedestrian indices]}.  Members are pulled next to the group's first member
+    (``spread`` metres apart, alternating sides) and walk roughly with it, so that gaze, coherence and
+    repulsion (contact at r_a + r_b = 0.7 m) are all exercised.  A lone tag (1 member) must stay inert."""
+    p, sc, lin, ang = _case(wl, seed, **scene_kw)
+    peds = sc.peds
+    for gid, members in groups.items():
+        lead = peds[members[0]]
+        for n, j in enumerate(members):
+            q = peds[j]
+            q["group_id"] = gid
+            if n == 0:
+                continue
+            q["x"] = lead["x"] + spread * n
+            q["y"] = lead["y"] + 0.3 * (-1) ** n
+            q["vx"] = lead["vx"] * (1.0 - 0.1 * n) + 0.05 * n
+            q["vy"] = lead["vy"] * (1.0 + 0.07 * n) - 0.04 * n
+            q["goal_x"] = q["x"] + 2.0 * q["vx"]
+            q["goal_y"] = q["y"] + 2.0 * q["vy"]
+    return p, sc, lin, ang
+
+
 C0 = S.WORKLOADS["C0"]
 CASES = {
     "c0_seed0": lambda: _case(C0, 0),
@@ -56,6 +79,13 @@ CASES = {
     "c1_shape_12x12": lambda: _case(dataclasses.replace(S.WORKLOADS["C1"], n_v=12, n_w=12), 0),
     "c3_shape_8x8": lambda: _case(dataclasses.replace(S.WORKLOADS["C3"], n_v=8, n_w=8), 7),
     "c4_shape_8x8": lambda: _case(dataclasses.replace(S.WORKLOADS["C4"], n_v=8, n_w=8), 0),
+    # pedestrian groups (lightsfm computeGroupForce through the computeForces call, sfw_planner.cpp:592)
+    "groups_pair_and_triple": lambda: _grouped(dataclasses.replace(C0, n_peds=7, steps=40), 2,
+                                               {3: [0, 1], 7: [2, 3, 4], 9: [5]}),
+    "groups_tight_contact": lambda: _grouped(dataclasses.replace(C0, n_peds=6, steps=32), 4,
+                                             {0: [0, 2, 4, 5]}, spread=0.3),
+    "groups_c1_shape_10x10": lambda: _grouped(dataclasses.replace(S.WORKLOADS["C1"], n_v=10, n_w=10), 1,
+                                              {1: [0, 1, 2], 2: [5, 9], 4: [10, 11, 12, 13, 14]}),
 }
 
 

@@ -216,3 +216,45 @@ def test_crowd_batch_and_slab(scorer):
         assert np.array_equal(c[0][b * 5:e * 5], costs[1][b * 5:e * 5])
         recs.append(bb[0])
     assert sharding.merge_winners(np.array(recs)) == best[1]
+
+
+@pytest.mark.parametrize("shift", [(0.0, 0.0), (-0.7, 0.0), (0.3, -1.07), (-0.75, 0.8)])
+def test_free_space_shortcut_at_map_edges(scorer, shift):
+    """The footprint check skips rasterisation where the whole +-fp_rc neighbourhood is free AND inside
+    the map.  A border-less 60x60 map (every edge cell cost 0) shifted so that rollouts leave it: only
+    the in-map test of the shortcut stands between a vertex off the map (-3 in the reference,
+    src/costmap_model.cpp:36,56-60) and a wrong "free" answer.  Plus isolated cost cells the footprint
+    outline may or may not touch."""
+    wl = dataclasses.replace(S.WORKLOADS["C0"], steps=40, map_w=60, map_h=60, n_peds=3)
+    sc = S.make_scene(wl, 2, n_obstacles=4)
+    cm = np.zeros((60, 60), dtype=np.uint8)
+    cm[30, 44] = 254   # on the straight path: 0.7 m ahead of the start pose
+    cm[37, 36] = 200   # inside the swept disc, high but legal
+    cm[22, 33] = 253   # inscribed-inflated value: allowed along footprint edges, rejected in point mode
+    cm[12, 12] = 255
+    sc.costmap = cm
+    sc.origin_x += shift[0]
+    sc.origin_y += shift[1]
+    p = wl.params()
+    lin, ang = wl.sample_arrays()
+    costs, best = scorer.score(p, [sc], lin, ang)
+    st = parity.compare(p, sc, lin, ang, costs[0], best[0])
+    if shift != (0.0, 0.0):
+        assert st["valid"] < st["n"] - 1, st  # some rollouts really do leave the map
+    print(shift, st)
+
+
+def test_crowd_kernel_with_groups(scorer):
+    """Group forces (lightsfm computeGroupForce) through the block-per-trajectory kernel."""
+    wl = dataclasses.replace(S.WORKLOADS["C2"], n_v=5, n_w=5, steps=24, n_peds=72, ped_r_max=6.0)
+    groups = {g: list(range(4 * g, 4 * g + 4)) for g in range(0, 12, 2)}
+    groups[40] = [60, 61]
+    groups[41] = [70]
+    p, sc, lin, ang = G._grouped(wl, 3, groups)
+    costs, best = scorer.score(p, [sc], lin, ang)
+    assert scorer.last_kernel == "sfw_score_crowd"
+    st = parity.compare(p, sc, lin, ang, costs[0], best[0], max_near_frac=1.0)
+    sc.peds["group_id"] = -1
+    costs0, _ = scorer.score(p, [sc], lin, ang)
+    assert not np.array_equal(costs0, costs), "group tags must change the result"
+    print(st)
