@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SFW_ABI_VERSION 1
+#define SFW_ABI_VERSION 2
 
 /* status codes */
 #define SFW_OK 0
@@ -198,6 +198,31 @@ int sfw_set_row_slab(sfw_ctx *ctx, uint32_t row_begin, uint32_t row_end);
  * points the rollout recorded in *n_points (stops at the first illegal pose like the reference). */
 int sfw_trajectory_points(sfw_ctx *ctx, uint32_t scene, uint32_t sample_index, double *xyz_out,
                           uint32_t max_points, uint32_t *n_points);
+
+/* ---- the step before the path: laser scan -> obstacle points ----------------------------------
+ * SFMSensorInterface::laserCb (reference src/sensor_interface.cpp:103-229): keep the beams that are
+ * finite and closer than max_obstacle_dist (:120-122), polar -> cartesian in FLOAT (:124-125; the
+ * scan angle is accumulated in float, :127), move them to the controller frame when the scan's frame
+ * differs (:143-170, the planar transform tf2 would apply is passed in), drop every point within
+ * person_radius (float hypot, :213-218) of a detected person, keep the beam order.  The surviving
+ * points are the obstacles1 list every agent of the scene carries (:513-524), i.e. SfwScene::
+ * obstacles_xy.  One block per scan; n_scans scans (one per scene of a batch) in one launch. */
+typedef struct SfwLaserScan {
+  const float *ranges;     /* sensor_msgs/LaserScan::ranges */
+  uint32_t n_ranges;
+  float angle_min, angle_increment;
+  int32_t has_tf;          /* 0: scan already in the controller frame */
+  double tf_x, tf_y, tf_yaw; /* laser frame -> controller frame */
+  const double *people_xy; /* n_people (x,y) pairs, controller frame (cpp:176-209) */
+  uint32_t n_people;
+  uint32_t reserved0;
+} SfwLaserScan;
+
+/* points_xy_out: n_scans slots of max_points_per_scan (x,y) pairs; n_points_out[n_scans] = points kept
+ * (never more than n_ranges; SFW_ERR_ARG if a slot is too small).  Synchronous. */
+int sfw_laser_obstacles(sfw_ctx *ctx, const SfwLaserScan *scans, uint32_t n_scans, float max_obstacle_dist,
+                        float person_radius, double *points_xy_out, uint32_t max_points_per_scan,
+                        uint32_t *n_points_out);
 
 /* ---- introspection (benchmark / interop) ---------------------------------------------------- */
 void *sfw_stream(sfw_ctx *ctx);                 /* cudaStream_t the context launches on */

@@ -731,3 +731,43 @@ int sfw_oracle_score_mt(const SfwParams *params, const SfwSfmParams *sfm, const 
     sfw_oracle_argmin(costs_out, linvels, n_v, angvels, n_w, best_out);
   return SFW_OK;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* SFMSensorInterface::laserCb — reference src/sensor_interface.cpp:103-229                     */
+/* ------------------------------------------------------------------------------------------ */
+uint32_t sfw_oracle_laser_obstacles(const SfwLaserScan *scan, float max_obstacle_dist, float person_radius,
+                                    double *points_xy_out) {
+  uint32_t n = 0;
+  float angle = scan->angle_min; /* :118 */
+  const double cs = cos(scan->tf_yaw), sn = sin(scan->tf_yaw);
+  for (uint32_t i = 0; i < scan->n_ranges; ++i) {
+    const float r = scan->ranges[i];
+    if (!isnan(r) && isfinite(r) && r < max_obstacle_dist) { /* :120-122 */
+      /* math.h is included before use (sensor_interface.hpp:52): cos(float) is the float overload */
+      double px = (double)(r * cosf(angle)), py = (double)(r * sinf(angle)); /* :124-125 */
+      if (scan->has_tf) { /* :143-170, tf2's transform restricted to the plane */
+        const double qx = cs * px - sn * py + scan->tf_x;
+        const double qy = sn * px + cs * py + scan->tf_y;
+        px = qx;
+        py = qy;
+      }
+      int remove = 0;
+      for (uint32_t q = 0; q < scan->n_people; ++q) { /* :210-225 */
+        const float dx = (float)(px - scan->people_xy[2 * q]);
+        const float dy = (float)(py - scan->people_xy[2 * q + 1]);
+        const float d = hypotf(dx, dy);
+        if (d <= person_radius) {
+          remove = 1;
+          break;
+        }
+      }
+      if (!remove) {
+        points_xy_out[2 * n] = px;
+        points_xy_out[2 * n + 1] = py;
+        ++n;
+      }
+    }
+    angle += scan->angle_increment; /* :127 */
+  }
+  return n;
+}

@@ -75,6 +75,12 @@ void sfw_oracle_pair_force(const SfwSfmParams *sfm, const double me[4], const do
 void sfw_oracle_obstacle_force(const SfwSfmParams *sfm, double px, double py, double radius,
                                const double *obstacles_xy, uint32_t n_obstacles, double out_fxy[2]);
 
+/* SFMSensorInterface::laserCb (reference src/sensor_interface.cpp:103-229): beams -> obstacle points of
+ * one scan, beam order kept.  points_xy_out must hold n_ranges pairs.  Returns the number kept.
+ * (The tf2 transform of :143-170 is external; it is restated as the planar rigid transform.) */
+uint32_t sfw_oracle_laser_obstacles(const SfwLaserScan *scan, float max_obstacle_dist, float person_radius,
+                                    double *points_xy_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,2 @@
+// empty stand-in (oracle/_ref sensor build only)
+#pragma once

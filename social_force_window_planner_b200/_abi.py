@@ -106,6 +106,21 @@ class SfwScene(C.Structure):
     ]
 
 
+class SfwLaserScan(C.Structure):
+    """One sensor_msgs/LaserScan as SFMSensorInterface::laserCb reads it (reference
+    src/sensor_interface.cpp:103-229) plus the people it is filtered against."""
+    _fields_ = [
+        ("ranges", C.POINTER(C.c_float)),
+        ("n_ranges", C.c_uint32),
+        ("angle_min", C.c_float), ("angle_increment", C.c_float),
+        ("has_tf", C.c_int32),
+        ("tf_x", C.c_double), ("tf_y", C.c_double), ("tf_yaw", C.c_double),
+        ("people_xy", C.POINTER(C.c_double)),
+        ("n_people", C.c_uint32),
+        ("reserved0", C.c_uint32),
+    ]
+
+
 class SfwBest(C.Structure):
     _fields_ = [
         ("valid", C.c_int32),

@@ -14,8 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsfw_b200.so")
-SOURCES = ["sfw_kernels.cu", "sfw_crowd.cu", "sfw_abi.cu"]
-HEADERS = ["sfw_dev.h", "sfw_kernels.h", "sfw_forces.cuh", os.path.join("..", "..", "include", "sfw_b200.h")]
+SOURCES = ["sfw_kernels.cu", "sfw_crowd.cu", "sfw_abi.cu", "sfw_sensor.cu"]
+HEADERS = ["sfw_dev.h", "sfw_kernels.h", "sfw_forces.cuh", "sfw_ctx.h", os.path.join("..", "..", "include", "sfw_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--shared", "-cudart", "static", "-diag-suppress", "177",
@@ -53,11 +53,13 @@ def build_host(force: bool = False) -> str:
     """libsfw_planner_host.so: the C++ mirror of the reference's SFWPlanner (host control flow + scene
     packer) linked against libsfw_b200.so."""
     build(force=False)
-    deps = [HOST_SRC, HOST_SRC.replace(".cpp", ".hpp"), os.path.join(HERE, "..", "include", "sfw_b200.h"), LIB]
+    sensor_src = os.path.join(HERE, "host", "sfw_sensor_host.cpp")
+    deps = [HOST_SRC, HOST_SRC.replace(".cpp", ".hpp"), sensor_src, sensor_src.replace(".cpp", ".hpp"),
+            os.path.join(HERE, "..", "include", "sfw_b200.h"), LIB]
     if not force and os.path.exists(HOST_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_LIB) for d in deps):
         return HOST_LIB
-    cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-Wextra", "-o", HOST_LIB,
-           HOST_SRC, "-L" + HERE, "-l:libsfw_b200.so", "-Wl,-rpath,$ORIGIN"]
+    cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wextra",
+           "-o", HOST_LIB, HOST_SRC, sensor_src, "-L" + HERE, "-l:libsfw_b200.so", "-Wl,-rpath,$ORIGIN"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -16,95 +16,29 @@
 #include <string>
 #include <vector>
 
+#include "sfw_ctx.h"
 #include "sfw_dev.h"
 #include "sfw_kernels.h"
 
 namespace {
 
-thread_local std::string g_create_error;
-
 constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-struct Arena {
-  uint8_t *host = nullptr; // pinned
-  uint8_t *dev = nullptr;
-  size_t cap = 0;
-};
-
-struct Plan {
-  // shape key
-  uint32_t n_scenes = 0, samples = 0, maxP = 0, maxM = 0, maxF = 0, win_wp = 0, win_h = 0;
-  // result
-  uint32_t T = 0, tiles = 0;
-  size_t smem = 0;
-  bool crowd = false; // block-per-trajectory kernel (sfw_crowd.cu)
-  uint32_t grid = 0;
-  int steps = 0;
-  bool valid = false;
-};
+typedef SfwPlan Plan;
+typedef SfwArena Arena;
 
 } // namespace
 
-struct sfw_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  bool own_stream = false;
-  int sm_count = 148;
-  std::string err;
-  std::mutex mu;
-
-  Arena in;   // packed inputs
-  Arena out;  // best | costs | npts | blockbest | counters
-  double *d_points = nullptr;
-  double *h_points = nullptr;
-  uint32_t points_cap = 0;
-
-  SfwBatchDev B;
-  CUtensorMap tmap;
-  bool staged = false, ran = false;
-  // tensor-map cache key
-  const void *tm_ptr = nullptr;
-  uint32_t tm_pitch = 0, tm_rows = 0, tm_scenes = 0, tm_wp = 0, tm_h = 0;
-  Plan plan;
-  size_t off_best = 0, off_costs = 0, off_npts = 0, off_bb = 0, off_cnt = 0, off_work = 0;
-  uint32_t out_scenes = 0, out_samples = 0, out_tiles = 0;
-  uint64_t launches = 0;
-  uint64_t algo_bytes = 0;
-  size_t in_bytes = 0;
-  const char *last_kernel = "none";
-  uint32_t slab_begin = 0, slab_end = 0xffffffffu;
-  std::vector<SfwSceneDev> scene_host; // host copy for trajectory_points
-};
-
-namespace {
-
-int fail(sfw_ctx *c, int code, const char *fmt, ...) {
-  char buf[512];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof(buf), fmt, ap);
-  va_end(ap);
-  if (c)
-    c->err = buf;
-  else
-    g_create_error = buf;
-  return code;
+std::string &sfw_create_error() {
+  thread_local std::string e;
+  return e;
 }
 
-#define CK(ctx, call)                                                                              \
-  do {                                                                                             \
-    cudaError_t e__ = (call);                                                                      \
-    if (e__ != cudaSuccess)                                                                        \
-      return fail((ctx), SFW_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),    \
-                  __FILE__, __LINE__);                                                             \
-  } while (0)
-
-int arena_reserve(sfw_ctx *c, Arena &a, size_t bytes) {
+int sfw_arena_reserve(sfw_ctx *c, SfwArena &a, size_t bytes) {
   if (bytes <= a.cap)
     return SFW_OK;
   // the stream may still be reading the old buffers
-  CK(c, cudaStreamSynchronize(c->stream));
+  SFW_CK(c, cudaStreamSynchronize(c->stream));
   if (a.host)
     cudaFreeHost(a.host);
   if (a.dev)
@@ -113,11 +47,17 @@ int arena_reserve(sfw_ctx *c, Arena &a, size_t bytes) {
   a.dev = nullptr;
   a.cap = 0;
   size_t cap = align_up(bytes + bytes / 4, 1 << 16);
-  CK(c, cudaMallocHost((void **)&a.host, cap));
-  CK(c, cudaMalloc((void **)&a.dev, cap));
+  SFW_CK(c, cudaMallocHost((void **)&a.host, cap));
+  SFW_CK(c, cudaMalloc((void **)&a.dev, cap));
   a.cap = cap;
   return SFW_OK;
 }
+
+namespace {
+
+#define fail sfw_fail
+#define CK SFW_CK
+#define arena_reserve sfw_arena_reserve
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                   const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -286,7 +226,7 @@ void sfw_default_sfm_params(SfwSfmParams *p) {
     *p = kDefaultSfm;
 }
 
-const char *sfw_last_error(const sfw_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+const char *sfw_last_error(const sfw_ctx *ctx) { return ctx ? ctx->err.c_str() : sfw_create_error().c_str(); }
 
 int sfw_create(sfw_ctx **out, int device, void *stream, const SfwLimits *limits) {
   if (!out)
@@ -332,7 +272,7 @@ int sfw_create(sfw_ctx **out, int device, void *stream, const SfwLimits *limits)
                     65536;
     size_t out_est = (size_t)limits->max_scenes * (sizeof(SfwBest) + (size_t)limits->max_samples * 6 + 4096);
     if (arena_reserve(c, c->in, in_est) != SFW_OK || arena_reserve(c, c->out, out_est) != SFW_OK) {
-      g_create_error = c->err;
+      sfw_create_error() = c->err;
       sfw_destroy(c);
       return SFW_ERR_CUDA;
     }
@@ -355,6 +295,12 @@ int sfw_destroy(sfw_ctx *c) {
     cudaFreeHost(c->out.host);
   if (c->out.dev)
     cudaFree(c->out.dev);
+  for (SfwArena *a : {&c->sensor_in, &c->sensor_out}) {
+    if (a->host)
+      cudaFreeHost(a->host);
+    if (a->dev)
+      cudaFree(a->dev);
+  }
   if (c->d_points)
     cudaFree(c->d_points);
   if (c->h_points)

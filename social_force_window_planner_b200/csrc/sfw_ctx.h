@@ -1,0 +1,93 @@
+// sfw_ctx.h — the context object behind the C ABI (include/sfw_b200.h), shared by the translation units
+// that implement entry points (sfw_abi.cu: scoring path, sfw_sensor.cu: laser scan -> obstacle points).
+#ifndef SFW_CTX_H
+#define SFW_CTX_H
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "sfw_dev.h"
+
+struct SfwArena {
+  uint8_t *host = nullptr; // pinned
+  uint8_t *dev = nullptr;
+  size_t cap = 0;
+};
+
+struct SfwPlan {
+  // shape key
+  uint32_t n_scenes = 0, samples = 0, maxP = 0, maxM = 0, maxF = 0, win_wp = 0, win_h = 0;
+  // result
+  uint32_t T = 0, tiles = 0;
+  size_t smem = 0;
+  bool crowd = false; // block-per-trajectory kernel (sfw_crowd.cu)
+  uint32_t grid = 0;
+  int steps = 0;
+  bool valid = false;
+};
+
+struct sfw_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  std::string err;
+  std::mutex mu;
+
+  SfwArena in;   // packed inputs
+  SfwArena out;  // best | costs | npts | blockbest | counters
+  SfwArena sensor_in, sensor_out; // sfw_laser_obstacles staging
+  double *d_points = nullptr;
+  double *h_points = nullptr;
+  uint32_t points_cap = 0;
+
+  SfwBatchDev B;
+  CUtensorMap tmap;
+  bool staged = false, ran = false;
+  // tensor-map cache key
+  const void *tm_ptr = nullptr;
+  uint32_t tm_pitch = 0, tm_rows = 0, tm_scenes = 0, tm_wp = 0, tm_h = 0;
+  SfwPlan plan;
+  size_t off_best = 0, off_costs = 0, off_npts = 0, off_bb = 0, off_cnt = 0, off_work = 0;
+  uint32_t out_scenes = 0, out_samples = 0, out_tiles = 0;
+  uint64_t launches = 0;
+  uint64_t algo_bytes = 0;
+  size_t in_bytes = 0;
+  const char *last_kernel = "none";
+  uint32_t slab_begin = 0, slab_end = 0xffffffffu;
+  std::vector<SfwSceneDev> scene_host; // host copy for trajectory_points
+};
+
+// error text of a failed sfw_create (no context to hang it on)
+std::string &sfw_create_error();
+
+inline int sfw_fail(sfw_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c)
+    c->err = buf;
+  else
+    sfw_create_error() = buf;
+  return code;
+}
+
+#define SFW_CK(ctx, call)                                                                          \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return sfw_fail((ctx), SFW_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                      __FILE__, __LINE__);                                                         \
+  } while (0)
+
+// grow a pinned-host + device buffer pair (contents are not preserved)
+int sfw_arena_reserve(sfw_ctx *c, SfwArena &a, size_t bytes);
+
+#endif

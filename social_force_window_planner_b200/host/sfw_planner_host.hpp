@@ -49,6 +49,8 @@ struct ControllerParams {
 struct Agent {
   int id = -1, groupId = -1;
   Point2D position, velocity;
+  double yaw = 0.0, linearVelocity = 0.0, angularVelocity = 0.0; // set by the sensor interface, unused by the scorer
+  bool teleoperated = false;
   double radius = 0.35, desiredVelocity = 0.6;
   bool has_goal = false;
   Point2D goal_center;

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._abi import BEST_DTYPE, SceneArray, SfwBest, SfwParams, SfwSfmParams
+from ._abi import BEST_DTYPE, SceneArray, SfwBest, SfwLaserScan, SfwParams, SfwSfmParams
 
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)
@@ -104,6 +104,38 @@ class Scorer:
         self._check(self._lib.sfw_trajectory_points(self._ctx, scene, sample_index,
                                                     buf.ctypes.data_as(_dp), max_points, C.byref(n)))
         return buf[: min(n.value, max_points)].copy(), n.value
+
+    # -- the step before the path: laser scans -> obstacle points ----------------------------------
+    def laser_obstacles(self, scans, max_obstacle_dist: float = 3.0, person_radius: float = 0.35):
+        """``sfw_laser_obstacles`` (SFMSensorInterface::laserCb, reference src/sensor_interface.cpp:103-229).
+
+        ``scans``: list of dicts ``ranges`` (float32[n]), ``angle_min``, ``angle_increment``, optional
+        ``tf`` = (x, y, yaw) laser->controller frame, optional ``people`` (float64[k, 2], controller
+        frame).  Returns one float64[m, 2] array of obstacle points per scan, beam order kept."""
+        arr = (SfwLaserScan * len(scans))()
+        keep = []
+        cap = 1
+        for a, sc in zip(arr, scans):
+            r = np.ascontiguousarray(sc["ranges"], dtype=np.float32)
+            ppl = np.ascontiguousarray(sc.get("people", np.zeros((0, 2))), dtype=np.float64).reshape(-1, 2)
+            keep += [r, ppl]
+            a.ranges = r.ctypes.data_as(_fp)
+            a.n_ranges = len(r)
+            a.angle_min = sc["angle_min"]
+            a.angle_increment = sc["angle_increment"]
+            tf = sc.get("tf")
+            a.has_tf = 1 if tf is not None else 0
+            if tf is not None:
+                a.tf_x, a.tf_y, a.tf_yaw = tf
+            a.people_xy = ppl.ctypes.data_as(_dp)
+            a.n_people = len(ppl)
+            cap = max(cap, len(r))
+        out = np.zeros((len(scans), cap, 2), dtype=np.float64)
+        cnt = np.zeros(len(scans), dtype=np.uint32)
+        self._check(self._lib.sfw_laser_obstacles(self._ctx, arr, len(scans), max_obstacle_dist, person_radius,
+                                                  out.ctypes.data_as(_dp), cap,
+                                                  cnt.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return [out[k, :cnt[k]].copy() for k in range(len(scans))]
 
     # -- introspection --------------------------------------------------------------------------
     @property

@@ -9,7 +9,7 @@ import subprocess
 
 import numpy as np
 
-from social_force_window_planner_b200._abi import (SceneArray, SfwBest, SfwParams, SfwScene,
+from social_force_window_planner_b200._abi import (SceneArray, SfwBest, SfwLaserScan, SfwParams, SfwScene,
                                                    SfwSfmParams)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -75,8 +75,30 @@ def oracle():
         lib.sfw_oracle_obstacle_force.restype = None
         lib.sfw_oracle_obstacle_force.argtypes = [C.POINTER(SfwSfmParams), C.c_double, C.c_double,
                                                   C.c_double, _dp, C.c_uint32, _dp]
+        lib.sfw_oracle_laser_obstacles.restype = C.c_uint32
+        lib.sfw_oracle_laser_obstacles.argtypes = [C.POINTER(SfwLaserScan), C.c_float, C.c_float, _dp]
         _oracle = lib
     return _oracle
+
+
+def oracle_laser_obstacles(scan: dict, max_obstacle_dist=3.0, person_radius=0.35):
+    """SFMSensorInterface::laserCb restated (oracle/sfw_oracle.c): obstacle points float64[m, 2] of one scan."""
+    r = np.ascontiguousarray(scan["ranges"], dtype=np.float32)
+    ppl = np.ascontiguousarray(scan.get("people", np.zeros((0, 2))), dtype=np.float64).reshape(-1, 2)
+    a = SfwLaserScan()
+    a.ranges = r.ctypes.data_as(C.POINTER(C.c_float))
+    a.n_ranges = len(r)
+    a.angle_min = scan["angle_min"]
+    a.angle_increment = scan["angle_increment"]
+    tf = scan.get("tf")
+    a.has_tf = 1 if tf is not None else 0
+    if tf is not None:
+        a.tf_x, a.tf_y, a.tf_yaw = tf
+    a.people_xy = ppl.ctypes.data_as(_dp)
+    a.n_people = len(ppl)
+    out = np.zeros((max(len(r), 1), 2), dtype=np.float64)
+    n = oracle().sfw_oracle_laser_obstacles(C.byref(a), max_obstacle_dist, person_radius, out.ctypes.data_as(_dp))
+    return out[:n].copy()
 
 
 def have_ref() -> bool:
@@ -106,6 +128,44 @@ def ref():
         lib.sfw_ref_default_samples.argtypes = [C.c_double, C.c_double, _dp, _dp]
         _ref = lib
     return _ref
+
+
+REF_SENSOR_SO = os.path.join(ORACLE_DIR, "_ref", "libsfw_ref_sensor.so")
+_ref_sensor = None
+
+
+def have_ref_sensor() -> bool:
+    return os.path.exists(REF_SENSOR_SO)
+
+
+def ref_sensor_run(scan: dict, people: np.ndarray, odom, params=(3.0, 0.35, 2.0, 1.0, 0.35, 0.7), people_has_tf=False):
+    """The reference's OWN SFMSensorInterface (src/sensor_interface.cpp compiled unmodified, oracle/_ref) on one
+    laser / people / odometry message set.  ``people``: float64[n, 8] rows {x, y, yaw, vx, vy, wz, id, group}
+    in the PEOPLE message frame; ``odom`` = (x, y, yaw, vx, vy, wz).  Returns (agents float64[n + 1, 16],
+    obstacle points float64[m, 2]) — see oracle/ref_sensor_harness.cpp for the agent columns."""
+    global _ref_sensor
+    if _ref_sensor is None:
+        lib = C.CDLL(REF_SENSOR_SO)
+        lib.sfw_ref_sensor_run.restype = C.c_int
+        lib.sfw_ref_sensor_run.argtypes = [C.POINTER(C.c_float), C.c_uint32, C.c_float, C.c_float, C.c_int, _dp,
+                                           C.c_uint32, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_uint32,
+                                           C.POINTER(C.c_uint32)]
+        _ref_sensor = lib
+    r = np.ascontiguousarray(scan["ranges"], dtype=np.float32)
+    ppl = np.ascontiguousarray(people, dtype=np.float64).reshape(-1, 8)
+    od = np.ascontiguousarray(odom, dtype=np.float64)
+    pr = np.ascontiguousarray(params, dtype=np.float64)
+    tf = np.ascontiguousarray(scan.get("tf") or (0.0, 0.0, 0.0), dtype=np.float64)
+    agents = np.zeros((len(ppl) + 1, 16), dtype=np.float64)
+    obs = np.zeros((max(len(r), 1), 2), dtype=np.float64)
+    n = C.c_uint32(0)
+    rc = _ref_sensor.sfw_ref_sensor_run(r.ctypes.data_as(C.POINTER(C.c_float)), len(r), scan["angle_min"],
+                                        scan["angle_increment"], 1 if scan.get("tf") is not None else 0,
+                                        ppl.ctypes.data_as(_dp), len(ppl), 1 if people_has_tf else 0,
+                                        od.ctypes.data_as(_dp), pr.ctypes.data_as(_dp), tf.ctypes.data_as(_dp),
+                                        agents.ctypes.data_as(_dp), obs.ctypes.data_as(_dp), len(obs), C.byref(n))
+    assert rc == 0
+    return agents, obs[:n.value].copy()
 
 
 def _d(a):
