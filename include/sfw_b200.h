@@ -199,6 +199,13 @@ int sfw_set_row_slab(sfw_ctx *ctx, uint32_t row_begin, uint32_t row_end);
 int sfw_trajectory_points(sfw_ctx *ctx, uint32_t scene, uint32_t sample_index, double *xyz_out,
                           uint32_t max_points, uint32_t *n_points);
 
+/* The same for many samples in one launch — the points of the RViz markers the reference fills for EVERY
+ * evaluated sample (src/sfw_planner.cpp:366-374): samples first, first + stride, ... (count of them) of one
+ * staged scene.  xyz_out: count slots of max_points (x,y,theta) triples; n_points_out[count]: points each
+ * rollout recorded (may exceed max_points; only min(n, max_points) triples are written). */
+int sfw_marker_points(sfw_ctx *ctx, uint32_t scene, uint32_t first, uint32_t stride, uint32_t count,
+                      double *xyz_out, uint32_t max_points, uint16_t *n_points_out);
+
 /* ---- the step before the path: laser scan -> obstacle points ----------------------------------
  * SFMSensorInterface::laserCb (reference src/sensor_interface.cpp:103-229): keep the beams that are
  * finite and closer than max_obstacle_dist (:120-122), polar -> cartesian in FLOAT (:124-125; the

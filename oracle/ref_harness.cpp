@@ -234,6 +234,46 @@ int sfw_ref_score(const SfwParams *params, const SfwSfmParams *sfm, const SfwSce
   return SFW_OK;
 }
 
+// The MarkerArray the reference's findBestAction leaves behind after one grid tick (:345-417,435-441):
+// per sample its colour (r,g,b,a), number of points and the points (x,y,z).  Same rig as sfw_ref_score.
+int sfw_ref_markers(const SfwParams *params, const SfwSfmParams *sfm, const SfwScene *scene,
+                    const double *linvels, uint32_t n_v, const double *angvels, uint32_t n_w, float *rgba_out,
+                    uint32_t *npts_out, double *xyz_out, uint32_t max_pts) {
+  auto rig = make_rig(*params, sfm, *scene);
+  SFWPlanner &pl = *rig->planner;
+  pl.params_.get(rig->node.get(), kName);
+  pl.linvels_.assign(linvels, linvels + n_v);
+  pl.angvels_.assign(angvels, angvels + n_w);
+  pl.initializeMarkers();
+  const SfwRobot &R = scene->robot;
+  std::vector<geometry_msgs::msg::PoseStamped> plan;
+  plan.push_back(pose_of(R.wpx, R.wpy, 0.0));
+  double d2 = (R.x - R.wpx) * (R.x - R.wpx) + (R.y - R.wpy) * (R.y - R.wpy);
+  if (d2 < 1.5 * 1.5 + 1e-9)
+    plan.push_back(pose_of(R.wpx + 100.0, R.wpy, 0.0));
+  pl.updatePlan(plan);
+  geometry_msgs::msg::Twist vel, cmd;
+  vel.linear.x = R.vx;
+  vel.linear.y = R.vy;
+  vel.angular.z = R.vtheta;
+  bool ok = pl.findBestAction(pose_of(R.x, R.y, R.theta), vel, cmd);
+  const auto &mk = pl.getMarkers().markers;
+  for (uint32_t i = 0; i < mk.size() && i < n_v * n_w; ++i) {
+    rgba_out[4 * i] = mk[i].color.r;
+    rgba_out[4 * i + 1] = mk[i].color.g;
+    rgba_out[4 * i + 2] = mk[i].color.b;
+    rgba_out[4 * i + 3] = mk[i].color.a;
+    npts_out[i] = (uint32_t)mk[i].points.size();
+    for (uint32_t k = 0; k < mk[i].points.size() && k < max_pts; ++k) {
+      double *o = xyz_out + ((size_t)i * max_pts + k) * 3;
+      o[0] = mk[i].points[k].x;
+      o[1] = mk[i].points[k].y;
+      o[2] = mk[i].points[k].z;
+    }
+  }
+  return ok ? 1 : 0;
+}
+
 // WorldModel::footprintCost(x,y,theta,spec) of the reference via SFWPlanner::footprintCost (:709).
 double sfw_ref_footprint_cost(const SfwScene *scene, double x, double y, double theta) {
   SfwParams p;

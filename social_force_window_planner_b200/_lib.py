@@ -19,7 +19,7 @@ EXPORTS = [
     "sfw_default_sfm_params", "sfw_score", "sfw_score_batch", "sfw_upload", "sfw_run",
     "sfw_download", "sfw_sync", "sfw_set_row_slab", "sfw_trajectory_points", "sfw_stream",
     "sfw_device_costs", "sfw_device_best", "sfw_kernel_launches", "sfw_algorithmic_bytes",
-    "sfw_last_kernel", "sfw_h2d_bytes", "sfw_d2h_bytes", "sfw_laser_obstacles",
+    "sfw_last_kernel", "sfw_h2d_bytes", "sfw_d2h_bytes", "sfw_laser_obstacles", "sfw_marker_points",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -79,6 +79,9 @@ def load() -> C.CDLL:
     lib.sfw_laser_obstacles.restype = C.c_int
     lib.sfw_laser_obstacles.argtypes = [_ctx, C.POINTER(SfwLaserScan), C.c_uint32, C.c_float, C.c_float, _dp,
                                         C.c_uint32, C.POINTER(C.c_uint32)]
+    lib.sfw_marker_points.restype = C.c_int
+    lib.sfw_marker_points.argtypes = [_ctx, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _dp, C.c_uint32,
+                                      C.POINTER(C.c_uint16)]
     lib.sfw_last_kernel.restype = C.c_char_p
     lib.sfw_last_kernel.argtypes = [_ctx]
     return lib

@@ -867,6 +867,39 @@ int sfw_trajectory_points(sfw_ctx *c, uint32_t scene, uint32_t sample_index, dou
   return SFW_OK;
 }
 
+int sfw_marker_points(sfw_ctx *c, uint32_t scene, uint32_t first, uint32_t stride, uint32_t count, double *xyz_out,
+                      uint32_t max_points, uint16_t *n_points_out) {
+  if (!c)
+    return SFW_ERR_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->ran)
+    return fail(c, SFW_ERR_STATE, "sfw_marker_points before sfw_run");
+  if (!count)
+    return SFW_OK;
+  if (!stride)
+    stride = 1;
+  if (scene >= c->B.n_scenes || !n_points_out || (!xyz_out && max_points) ||
+      (uint64_t)first + (uint64_t)(count - 1) * stride >= c->out_samples)
+    return fail(c, SFW_ERR_ARG, "sfw_marker_points: sample range out of bounds");
+  CK(c, cudaSetDevice(c->device));
+  const size_t o_n = 0, o_xyz = align_up(2 * (size_t)count, kAlign);
+  const size_t bytes = o_xyz + 24 * (size_t)count * max_points;
+  int rc = arena_reserve(c, c->sensor_out, bytes); // scratch arena (shared with the laser path)
+  if (rc != SFW_OK)
+    return rc;
+  uint8_t *dv = c->sensor_out.dev, *hv = c->sensor_out.host;
+  CK(c, sfw_launch_marker_points(c->B, scene, first, stride, count, max_points,
+                                 reinterpret_cast<double *>(dv + o_xyz), reinterpret_cast<uint16_t *>(dv + o_n),
+                                 c->stream));
+  c->launches += 1;
+  CK(c, cudaMemcpyAsync(hv, dv, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  memcpy(n_points_out, hv + o_n, 2 * (size_t)count);
+  if (max_points)
+    memcpy(xyz_out, hv + o_xyz, 24 * (size_t)count * max_points);
+  return SFW_OK;
+}
+
 void *sfw_stream(sfw_ctx *c) { return c ? (void *)c->stream : nullptr; }
 const float *sfw_device_costs(sfw_ctx *c) { return (c && c->staged) ? c->B.costs : nullptr; }
 const void *sfw_device_best(sfw_ctx *c) { return (c && c->staged) ? (const void *)c->B.best : nullptr; }

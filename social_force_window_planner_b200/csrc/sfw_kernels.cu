@@ -554,6 +554,45 @@ extern "C" __global__ void sfw_points_kernel(const __grid_constant__ SfwBatchDev
   }
 }
 
+// The same replay for many samples at once (RViz markers, reference src/sfw_planner.cpp:366-374): thread t
+// handles sample first + t * stride and writes its recorded points to out_xyz[t][max_points][3].
+extern "C" __global__ void sfw_marker_points_kernel(const __grid_constant__ SfwBatchDev B, uint32_t scene,
+                                                    uint32_t first, uint32_t stride, uint32_t count,
+                                                    uint32_t max_points, double *out_xyz, uint16_t *out_n) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count)
+    return;
+  const uint32_t idx = first + t * stride;
+  const SfwSceneDev *scp = B.scenes + scene;
+  const uint32_t n_rec = B.npts[(size_t)scene * B.n_v * B.n_w + idx];
+  out_n[t] = (uint16_t)n_rec;
+  const uint32_t n_points = min(n_rec, max_points);
+  const double v_s = B.linvels[idx / B.n_w], w_s = B.angvels[idx % B.n_w];
+  double x = scp->rx, y = scp->ry, th = scp->rth, vx = scp->rvx, vth = scp->rvth;
+  const double vy = scp->rvy, dt = B.dt;
+  const double ax_dt = __dmul_rn(B.acc_x, dt), ath_dt = __dmul_rn(B.acc_th, dt);
+  double *o = out_xyz + (size_t)t * max_points * 3u;
+  for (uint32_t i = 0; i < n_points; ++i) {
+    o[3 * i] = x;
+    o[3 * i + 1] = y;
+    o[3 * i + 2] = th;
+    double sn, cs;
+    sincos(th, &sn, &cs);
+    vx = step_velocity(v_s, vx, ax_dt);
+    vth = step_velocity(w_s, vth, ath_dt);
+    double lx = __dmul_rn(vx, cs), ly = __dmul_rn(vx, sn);
+    if (vy != 0.0) {
+      double sn2, cs2;
+      sincos(__dadd_rn(1.57079632679489661923, th), &sn2, &cs2);
+      lx = __dadd_rn(lx, __dmul_rn(vy, cs2));
+      ly = __dadd_rn(ly, __dmul_rn(vy, sn2));
+    }
+    x = __dadd_rn(x, __dmul_rn(lx, dt));
+    y = __dadd_rn(y, __dmul_rn(ly, dt));
+    th = __dadd_rn(th, __dmul_rn(vth, dt));
+  }
+}
+
 // ================================================================================================
 // launch wrappers (called from sfw_abi.cu)
 // ================================================================================================
@@ -642,3 +681,11 @@ cudaError_t sfw_launch_points(const SfwBatchDev &B, uint32_t scene, uint32_t idx
   return cudaGetLastError();
 }
 
+
+cudaError_t sfw_launch_marker_points(const SfwBatchDev &B, uint32_t scene, uint32_t first, uint32_t stride,
+                                     uint32_t count, uint32_t max_points, double *out_xyz, uint16_t *out_n,
+                                     cudaStream_t stream) {
+  sfw_marker_points_kernel<<<(count + 127u) / 128u, 128, 0, stream>>>(B, scene, first, stride, count, max_points,
+                                                                    out_xyz, out_n);
+  return cudaGetLastError();
+}

@@ -20,4 +20,7 @@ cudaError_t sfw_launch_crowd(const SfwBatchDev &B, unsigned int *work_counter, u
                              cudaStream_t stream);
 cudaError_t sfw_launch_points(const SfwBatchDev &B, uint32_t scene, uint32_t idx, uint32_t n_points,
                               double *out_xyz, cudaStream_t stream);
+cudaError_t sfw_launch_marker_points(const SfwBatchDev &B, uint32_t scene, uint32_t first, uint32_t stride,
+                                     uint32_t count, uint32_t max_points, double *out_xyz, uint16_t *out_n,
+                                     cudaStream_t stream);
 #endif

@@ -2,6 +2,7 @@
 // SFWPlanner::findBestAction around ONE call into the CUDA scorer per tick.
 #include "sfw_planner_host.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -167,6 +168,54 @@ std::vector<Point2D> SFWPlanner::trajectoryPoints(uint32_t sample_index) {
   for (uint32_t i = 0; i < n; ++i) {
     out[i].x = xyz[3 * i];
     out[i].y = xyz[3 * i + 1];
+  }
+  return out;
+}
+
+std::vector<Marker> SFWPlanner::getMarkerArray() {
+  std::vector<Marker> out;
+  const size_t n = linvels_.size() * angvels_.size();
+  if (!ctx_ || !staged_ || costs_.size() != n)
+    return out; // no grid tick yet (the approach / rotate branches leave the markers alone)
+  out.resize(n);
+  std::vector<uint16_t> npts(n);
+  uint32_t max_pts = 1;
+  // first pass: counts only; second: the points
+  if (sfw_marker_points(ctx_, 0, 0, 1, (uint32_t)n, nullptr, 0, npts.data()) != SFW_OK) {
+    error_ = sfw_last_error(ctx_);
+    out.clear();
+    return out;
+  }
+  for (uint16_t v : npts)
+    max_pts = std::max<uint32_t>(max_pts, v);
+  std::vector<double> xyz(3 * (size_t)max_pts * n);
+  if (sfw_marker_points(ctx_, 0, 0, 1, (uint32_t)n, xyz.data(), max_pts, npts.data()) != SFW_OK) {
+    error_ = sfw_last_error(ctx_);
+    out.clear();
+    return out;
+  }
+  for (size_t i = 0; i < n; ++i) {
+    Marker &m = out[i];
+    m.id = (int)i;
+    if (costs_[i] == SFW_COST_SKIPPED)
+      continue; // :349-352
+    m.points_xyz.resize(3 * (size_t)npts[i]);
+    for (uint32_t k = 0; k < npts[i]; ++k) {
+      m.points_xyz[3 * k] = xyz[((size_t)i * max_pts + k) * 3];
+      m.points_xyz[3 * k + 1] = xyz[((size_t)i * max_pts + k) * 3 + 1];
+      m.points_xyz[3 * k + 2] = 0.0;
+    }
+    if (costs_[i] < 0.0f) { // :376-386
+      m.r = 1.0f, m.g = 0.0f, m.b = 0.0f, m.a = 0.6f;
+    } else {
+      m.r = 0.0f, m.g = 0.0f, m.b = 1.0f, m.a = 0.6f;
+    }
+  }
+  if (best_i_ >= 0 && (size_t)best_i_ < n) { // :435-441
+    Marker &m = out[best_i_];
+    for (size_t k = 0; k < m.points_xyz.size() / 3; ++k)
+      m.points_xyz[3 * k + 2] = 0.1;
+    m.r = 0.0f, m.g = 1.0f, m.b = 0.0f, m.a = 1.0f;
   }
   return out;
 }
@@ -468,6 +517,25 @@ int sfwh_find_best_action(sfwh_planner *h, const double *pose_xyt, const double 
   if (launches)
     *launches = h->pl->kernelLaunches();
   return ok ? 1 : 0;
+}
+
+// MarkerArray of the last grid tick: rgba_out[n*4], npts_out[n], xyz_out[n*max_pts*3]; returns n or -1
+int sfwh_get_markers(sfwh_planner *h, float *rgba_out, uint32_t *npts_out, double *xyz_out, uint32_t max_pts) {
+  std::vector<social_force_window_planner::Marker> mk = h->pl->getMarkerArray();
+  if (mk.empty())
+    return -1;
+  for (size_t i = 0; i < mk.size(); ++i) {
+    rgba_out[4 * i] = mk[i].r;
+    rgba_out[4 * i + 1] = mk[i].g;
+    rgba_out[4 * i + 2] = mk[i].b;
+    rgba_out[4 * i + 3] = mk[i].a;
+    const size_t np = mk[i].points_xyz.size() / 3;
+    npts_out[i] = (uint32_t)np;
+    for (size_t k = 0; k < np && k < max_pts; ++k)
+      for (int c = 0; c < 3; ++c)
+        xyz_out[(i * max_pts + k) * 3 + c] = mk[i].points_xyz[3 * k + c];
+  }
+  return (int)mk.size();
 }
 
 int sfwh_is_goal_reached(sfwh_planner *h) { return h->pl->isGoalReached() ? 1 : 0; }

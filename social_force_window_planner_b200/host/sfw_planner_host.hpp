@@ -72,6 +72,14 @@ struct SampleMarker {
   float cost = 0.0f; // < 0: rejected (red in the reference), >= 0 valid, best one green
 };
 
+// visualization_msgs::msg::Marker as the planner fills it (reference src/sfw_planner.cpp:91-110,345-386,
+// 435-441): id = sample index, LINE_STRIP of the rollout's recorded points, colour by outcome
+struct Marker {
+  int id = 0;
+  float r = 0.f, g = 0.f, b = 0.f, a = 1.0f; // initializeMarkers: colour (0,0,0,1)
+  std::vector<double> points_xyz;            // (x, y, z) triples
+};
+
 class SFWPlanner {
 public:
   // reference ctor (sfw_planner.cpp:28-87): params, costmap reference, footprint; builds the 5 x 9
@@ -102,6 +110,10 @@ public:
   // and the recorded rollout points of any sample of the last tick
   const std::vector<SampleMarker> &getMarkers() const { return markers_; }
   int bestIndex() const { return best_i_; }
+  // the whole MarkerArray of the last grid tick, as getMarkers() returns it in the reference: one marker per
+  // sample with the rollout's recorded points (one sfw_marker_points launch), red = rejected, blue = valid,
+  // green + raised to z = 0.1 = the chosen one; the skipped (0,0) sample keeps the initial colour, no points
+  std::vector<Marker> getMarkerArray();
   std::vector<Point2D> trajectoryPoints(uint32_t sample_index);
 
   // introspection for tests

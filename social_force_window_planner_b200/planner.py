@@ -105,6 +105,22 @@ class SFWPlanner:
         self.wp_index, self.running, self.best_index, self.kernel_launches = wp.value, bool(run.value), bi.value, nl.value
         return bool(ok), tuple(cmd)
 
+    def getMarkers(self, n_samples: int, max_points: int = 128):
+        """The MarkerArray of the last grid tick (reference getMarkers(), src/sfw_planner.cpp:112-114):
+        (rgba float32[n, 4], n_points uint32[n], xyz float64[n, max_points, 3]) or None before a grid tick."""
+        h = self._h
+        h.sfwh_get_markers.restype = C.c_int
+        h.sfwh_get_markers.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint32), _dp, C.c_uint32]
+        rgba = np.zeros((n_samples, 4), dtype=np.float32)
+        npts = np.zeros(n_samples, dtype=np.uint32)
+        xyz = np.zeros((n_samples, max_points, 3), dtype=np.float64)
+        n = h.sfwh_get_markers(self._p, rgba.ctypes.data_as(C.POINTER(C.c_float)),
+                               npts.ctypes.data_as(C.POINTER(C.c_uint32)), xyz.ctypes.data_as(_dp), max_points)
+        if n < 0:
+            return None
+        assert n == n_samples
+        return rgba, npts, xyz
+
     def isGoalReached(self) -> bool:
         return bool(self._h.sfwh_is_goal_reached(self._p))
 

@@ -105,6 +105,20 @@ class Scorer:
                                                     buf.ctypes.data_as(_dp), max_points, C.byref(n)))
         return buf[: min(n.value, max_points)].copy(), n.value
 
+    def marker_points(self, scene: int, first: int = 0, stride: int = 1, count: int | None = None,
+                      max_points: int | None = None):
+        """``sfw_marker_points``: recorded rollout points of samples first, first+stride, ... in one launch.
+        Returns (xyz float64[count, max_points, 3], n_points uint16[count])."""
+        if count is None:
+            count = (self.n_samples - first + stride - 1) // stride
+        if max_points is None:
+            max_points = 256
+        xyz = np.zeros((count, max_points, 3), dtype=np.float64)
+        n = np.zeros(count, dtype=np.uint16)
+        self._check(self._lib.sfw_marker_points(self._ctx, scene, first, stride, count, xyz.ctypes.data_as(_dp),
+                                                max_points, n.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return xyz, n
+
     # -- the step before the path: laser scans -> obstacle points ----------------------------------
     def laser_obstacles(self, scans, max_obstacle_dist: float = 3.0, person_radius: float = 0.35):
         """``sfw_laser_obstacles`` (SFMSensorInterface::laserCb, reference src/sensor_interface.cpp:103-229).

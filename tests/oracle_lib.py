@@ -124,6 +124,10 @@ def ref():
                                                  C.POINTER(SfwScene), _dp, C.c_uint32, _dp, C.c_uint32,
                                                  _dp, C.c_uint32, _dp, C.POINTER(C.c_int),
                                                  C.POINTER(C.c_int)]
+        lib.sfw_ref_markers.restype = C.c_int
+        lib.sfw_ref_markers.argtypes = [C.POINTER(SfwParams), C.POINTER(SfwSfmParams), C.POINTER(SfwScene), _dp,
+                                        C.c_uint32, _dp, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint32),
+                                        _dp, C.c_uint32]
         lib.sfw_ref_default_samples.restype = C.c_int
         lib.sfw_ref_default_samples.argtypes = [C.c_double, C.c_double, _dp, _dp]
         _ref = lib
@@ -166,6 +170,20 @@ def ref_sensor_run(scan: dict, people: np.ndarray, odom, params=(3.0, 0.35, 2.0,
                                         agents.ctypes.data_as(_dp), obs.ctypes.data_as(_dp), len(obs), C.byref(n))
     assert rc == 0
     return agents, obs[:n.value].copy()
+
+
+def ref_markers(params, scene, linvels, angvels, max_points=128, sfm=None):
+    """MarkerArray the reference's findBestAction leaves after one grid tick: (ok, rgba[n,4], npts[n], xyz[n,max,3])."""
+    sa = SceneArray([scene])
+    lin, ang = _d(linvels), _d(angvels)
+    n = len(lin) * len(ang)
+    rgba = np.zeros((n, 4), dtype=np.float32)
+    npts = np.zeros(n, dtype=np.uint32)
+    xyz = np.zeros((n, max_points, 3), dtype=np.float64)
+    ok = ref().sfw_ref_markers(C.byref(params), C.byref(sfm) if sfm else None, sa.ptr(0), lin.ctypes.data_as(_dp),
+                               len(lin), ang.ctypes.data_as(_dp), len(ang), rgba.ctypes.data_as(C.POINTER(C.c_float)),
+                               npts.ctypes.data_as(C.POINTER(C.c_uint32)), xyz.ctypes.data_as(_dp), max_points)
+    return bool(ok), rgba, npts, xyz
 
 
 def _d(a):

@@ -4,6 +4,7 @@ tick) against what the reference's own findBestAction returned for the same scen
 import json
 import os
 
+import numpy as np
 import pytest
 
 import host_cases as H
@@ -19,3 +20,40 @@ def test_find_best_action_matches_reference(name):
     assert (ok, list(cmd), wp, running) == (g["ok"], g["cmd"], g["wp_index"], g["running"]), (name, err)
     needs_gpu = H.CASES[name][3]
     assert (launches > 0) == needs_gpu
+
+
+MARKER_GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "marker_golden.npz"))
+
+
+@pytest.mark.parametrize("name", sorted({k.split("/")[0] for k in MARKER_GOLD.files}))
+def test_marker_array_matches_reference(name):
+    """getMarkers() of the host mirror after one grid tick against the MarkerArray the reference's own
+    findBestAction produced (committed fixture): colours identical, recorded points bit-identical (FP64
+    rollout), winner raised to z = 0.1.  The points of all samples come from ONE sfw_marker_points launch."""
+    import golden_cases as G
+    from social_force_window_planner_b200.planner import SFWPlanner
+    p, sc, lin, ang = G.CASES[name]()
+    pl = SFWPlanner(p, sc)
+    try:
+        pl.setSampleSets(lin, ang)
+        r = sc.robot
+        # same plan the harness builds: one pose at the waypoint, a far goal when the waypoint is near
+        plan = [(r[6], r[7], 0.0)]
+        if (r[0] - r[6]) ** 2 + (r[1] - r[7]) ** 2 < 1.5 * 1.5 + 1e-9:
+            plan.append((r[6] + 100.0, r[7], 0.0))
+        pl.updatePlan(plan)
+        ok, cmd = pl.findBestAction((r[0], r[1], r[2]), (r[3], r[4], r[5]))
+        rgba, npts, xyz = pl.getMarkers(len(lin) * len(ang), max_points=64)
+    finally:
+        pl.close()
+    assert ok == bool(MARKER_GOLD[name + "/ok"][0])
+    assert np.array_equal(rgba, MARKER_GOLD[name + "/rgba"])
+    assert np.array_equal(npts, MARKER_GOLD[name + "/npts"])
+    # The rollout is the same FP64 expression sequence as the reference's; the only foreign ingredient is
+    # sin/cos (CUDA's double sincos is within 1 ulp, glibc's is almost always correctly rounded), so a pose
+    # may differ in its last bit where the two libraries round differently.
+    gold = MARKER_GOLD[name + "/xyz"]
+    diff = np.abs(xyz - gold)
+    print(name, "points differing in the last bits:", int((diff > 0).sum()), "of", int(3 * npts.sum()), "max", diff.max())
+    assert diff.max() <= 1e-14
+    assert (diff > 0).sum() <= 0.05 * 3 * npts.sum() + 1
