@@ -31,7 +31,9 @@ struct ScanDev {
 __global__ void __launch_bounds__(kThreads)
 sfw_laser_kernel(const ScanDev *__restrict__ scans, const float *__restrict__ ranges,
                  const double2 *__restrict__ people, float max_dist, float person_radius,
-                 double2 *__restrict__ out, uint32_t slot, uint32_t *__restrict__ n_out) {
+                 double2 *__restrict__ out, uint32_t slot, uint32_t *__restrict__ n_out,
+                 double2 *__restrict__ compact, uint32_t *__restrict__ compact_off,
+                 unsigned int *__restrict__ compact_fill) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ScanDev sc = scans[blockIdx.x];
   float *s_angle = reinterpret_cast<float *>(smem);                                      // [n_ranges]
@@ -101,8 +103,18 @@ sfw_laser_kernel(const ScanDev *__restrict__ scans, const float *__restrict__ ra
     }
     __syncthreads();
   }
-  if (tid == 0)
-    n_out[blockIdx.x] = s_base;
+  // Second copy of the survivors into one dense buffer (a range reserved with one atomic per scan), so the
+  // host fetches sum(kept) points with a single D2H instead of one copy per scan.
+  const uint32_t kept = s_base;
+  if (tid == 0) {
+    n_out[blockIdx.x] = kept;
+    s_warp[0] = kept ? atomicAdd(compact_fill, kept) : 0u;
+    compact_off[blockIdx.x] = s_warp[0];
+  }
+  __syncthreads();
+  const uint32_t base = s_warp[0];
+  for (uint32_t i = tid; i < kept; i += kThreads)
+    compact[base + i] = dst[i];
 }
 
 } // namespace
@@ -136,7 +148,9 @@ extern "C" int sfw_laser_obstacles(sfw_ctx *c, const SfwLaserScan *scans, uint32
   const size_t o_scan = 0, o_rng = up(sizeof(ScanDev) * n_scans), o_ppl = o_rng + up(4 * tot_r);
   const size_t in_bytes = o_ppl + up(16 * tot_p);
   const size_t slot = max_points_per_scan;
-  const size_t o_cnt = 0, o_pts = up(4 * (size_t)n_scans), out_bytes = o_pts + 16 * slot * n_scans;
+  // out arena: counts | dense offsets | fill counter | dense points | per-scan slots
+  const size_t o_cnt = 0, o_off = up(4 * (size_t)n_scans), o_fill = o_off + up(4 * (size_t)n_scans);
+  const size_t o_dense = o_fill + 256, o_pts = o_dense + up(16 * tot_r), out_bytes = o_pts + 16 * slot * n_scans;
   int rc = sfw_arena_reserve(c, c->sensor_in, in_bytes);
   if (rc != SFW_OK)
     return rc;
@@ -177,27 +191,31 @@ extern "C" int sfw_laser_obstacles(sfw_ctx *c, const SfwLaserScan *scans, uint32
     attr_done = true;
   }
   uint8_t *dv = c->sensor_in.dev, *dout = c->sensor_out.dev;
+  SFW_CK(c, cudaMemsetAsync(dout + o_fill, 0, 4, c->stream));
   sfw_laser_kernel<<<n_scans, kThreads, smem, c->stream>>>(
       reinterpret_cast<const ScanDev *>(dv + o_scan), reinterpret_cast<const float *>(dv + o_rng),
       reinterpret_cast<const double2 *>(dv + o_ppl), max_obstacle_dist, person_radius,
-      reinterpret_cast<double2 *>(dout + o_pts), (uint32_t)slot, reinterpret_cast<uint32_t *>(dout + o_cnt));
+      reinterpret_cast<double2 *>(dout + o_pts), (uint32_t)slot, reinterpret_cast<uint32_t *>(dout + o_cnt),
+      reinterpret_cast<double2 *>(dout + o_dense), reinterpret_cast<uint32_t *>(dout + o_off),
+      reinterpret_cast<unsigned int *>(dout + o_fill));
   SFW_CK(c, cudaGetLastError());
   c->launches += 1;
   c->last_kernel = "sfw_laser_kernel";
-  // counts first, then only the kept points of every scan
-  SFW_CK(c, cudaMemcpyAsync(c->sensor_out.host + o_cnt, dout + o_cnt, 4 * (size_t)n_scans, cudaMemcpyDeviceToHost,
-                            c->stream));
+  // counts + dense offsets + total first, then the dense points in one copy
+  SFW_CK(c, cudaMemcpyAsync(c->sensor_out.host + o_cnt, dout + o_cnt, o_dense, cudaMemcpyDeviceToHost, c->stream));
   SFW_CK(c, cudaStreamSynchronize(c->stream));
   const uint32_t *cnt = reinterpret_cast<const uint32_t *>(c->sensor_out.host + o_cnt);
-  for (uint32_t s = 0; s < n_scans; ++s)
-    if (cnt[s])
-      SFW_CK(c, cudaMemcpyAsync(c->sensor_out.host + o_pts + 16 * slot * s, dout + o_pts + 16 * slot * s,
-                                16 * (size_t)cnt[s], cudaMemcpyDeviceToHost, c->stream));
-  SFW_CK(c, cudaStreamSynchronize(c->stream));
+  const uint32_t *offs = reinterpret_cast<const uint32_t *>(c->sensor_out.host + o_off);
+  const uint32_t total = *reinterpret_cast<const uint32_t *>(c->sensor_out.host + o_fill);
+  if (total) {
+    SFW_CK(c, cudaMemcpyAsync(c->sensor_out.host + o_dense, dout + o_dense, 16 * (size_t)total, cudaMemcpyDeviceToHost,
+                              c->stream));
+    SFW_CK(c, cudaStreamSynchronize(c->stream));
+  }
   for (uint32_t s = 0; s < n_scans; ++s) {
     n_points_out[s] = cnt[s];
     if (cnt[s])
-      memcpy(points_xy_out + 2 * slot * s, c->sensor_out.host + o_pts + 16 * slot * s, 16 * (size_t)cnt[s]);
+      memcpy(points_xy_out + 2 * slot * s, c->sensor_out.host + o_dense + 16 * (size_t)offs[s], 16 * (size_t)cnt[s]);
   }
   return SFW_OK;
 }
