@@ -96,7 +96,7 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
   const uint32_t per_scene = (B.row_end - B.row_begin) * n_w;
   const uint32_t total = B.n_scenes * per_scene;
   const int S = B.num_steps;
-  const SfmConst K = {B.lambda, B.c_d, B.gamma * B.gamma, B.c_np, B.c_n, B.k_soc};
+  const SfmConst K = make_sfm_const(B);
   const double dt = B.dt;
   const double ax_dt = __dmul_rn(B.acc_x, dt), ath_dt = __dmul_rn(B.acc_th, dt);
   const float dtf = B.dtf;

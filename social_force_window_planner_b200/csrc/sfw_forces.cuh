@@ -146,35 +146,49 @@ __device__ __forceinline__ f2 rsqrt2(f2 a) {
 // sign.  With I = lambda*vd + e (unnormalised), L = |I|:  I x e = lambda * (vd x e)  exactly, so the
 // sine is formed from the velocity difference — no cancellation, and EXACTLY zero when the two
 // velocities are equal, where lightsfm gets theta == 0 and switches the angular term off.
-// |theta| = asin(min(|sin|,|cos|)) folded back by quadrant; asin on [0, 1/sqrt 2] is an 8-term odd
-// minimax polynomial (|err| < 1e-7, fit in DESIGN.md), so no division and one MUFU less than atan2.
+// |theta| = asin(min(|sin|,|cos|)) folded back by quadrant; asin on [0, 1/sqrt 2] is a 7-term odd
+// minimax polynomial (|err| < 1.3e-7 in FP32), so no division and one MUFU less than atan2.
 // ------------------------------------------------------------------------------------------------
 struct SfmConst {
   float lambda, c_d, g2, c_np, c_n, k_soc; // g2 = gamma^2
+  float kq_v, kq_a;                        // c_np * g2, c_n * g2: exponent = -c_d |d|/L - kq (L theta)^2
 };
+__device__ __forceinline__ SfmConst make_sfm_const(const SfwBatchDev &B) {
+  SfmConst K;
+  K.lambda = B.lambda;
+  K.c_d = B.c_d;
+  K.g2 = B.gamma * B.gamma;
+  K.c_np = B.c_np;
+  K.c_n = B.c_n;
+  K.k_soc = B.k_soc;
+  K.kq_v = B.c_np * K.g2;
+  K.kq_a = B.c_n * K.g2;
+  return K;
+}
 
-#define SFW_ASIN_C0 0.9999998211860657f
-#define SFW_ASIN_C1 0.16668058931827545f
-#define SFW_ASIN_C2 0.0746382400393486f
-#define SFW_ASIN_C3 0.04882850497961044f
-#define SFW_ASIN_C4 0.005111650098115206f
-#define SFW_ASIN_C5 0.10628256946802139f
-#define SFW_ASIN_C6 -0.13144730031490326f
-#define SFW_ASIN_C7 0.13190637528896332f
+// asin(m)/m on m^2 in [0, 1/2]: 7-coefficient minimax (|err| of asin < 8e-8 exact, 1.3e-7 in FP32 Horner)
+#define SFW_ASIN_C0 1.0000001192092896f
+#define SFW_ASIN_C1 0.1666467934846878f
+#define SFW_ASIN_C2 0.0755898728966713f
+#define SFW_ASIN_C3 0.03815845027565956f
+#define SFW_ASIN_C4 0.06345300376415253f
+#define SFW_ASIN_C5 -0.05950368940830231f
+#define SFW_ASIN_C6 0.10390560328960419f
 
 // quadrant fold: phi = asin(min(|s|,|c|)) in [0, pi/4] -> |theta| in [0, pi]
 __device__ __forceinline__ float fold_theta(float phi, float asn, float acs, float cs) {
   float th = (asn > acs) ? (1.5707963267948966f - phi) : phi;
   return (cs < 0.0f) ? (3.14159265358979f - th) : th;
 }
-// -sign(theta) * mag with lightsfm's Angle::sign(): 0 only for theta == 0, +1 for theta == pi
+// +sign(theta) * |mag| with lightsfm's Angle::sign(): 0 only for theta == 0, +1 for theta == pi
 // (mag may carry any sign; only its magnitude is used)
 __device__ __forceinline__ float signed_angle_term(float mag, float sn, float cs) {
   float fa = __uint_as_float((__float_as_uint(mag) & 0x7fffffffu) | (__float_as_uint(sn) & 0x80000000u));
   if (sn == 0.0f)
     fa = (cs < 0.0f) ? fabsf(mag) : 0.0f;
-  return fa; // = +sign(theta) * |mag|
+  return fa;
 }
+__device__ __forceinline__ float flip_sign(float v) { return __uint_as_float(__float_as_uint(v) ^ 0x80000000u); }
 
 // scalar version (diagonal pairs, last-step pass)
 template <bool WITH_MAG>
@@ -185,18 +199,17 @@ __device__ __forceinline__ void pair_force(const SfmConst &K, float ax, float ay
   const float d2 = fmaf(dx, dx, fmaf(dy, dy, 1e-30f));    // +eps: coincident agents give 0, not NaN
   const float rd = rsqrt_approx(d2);
   const float ex = dx * rd, ey = dy * rd;                 // diffDirection
-  const float vdx = avx - bvx, vdy = avy - bvy;
+  const float vdx = avx - bvx, nvdy = bvy - avy;          // velocity difference (y negated)
   const float ix = fmaf(K.lambda, vdx, ex);               // interactionVector
-  const float iy = fmaf(K.lambda, vdy, ey);
+  const float iy = fmaf(-K.lambda, nvdy, ey);
   const float L2 = fmaf(ix, ix, fmaf(iy, iy, 1e-30f));
   const float rL = rsqrt_approx(L2);                      // 1 / interactionLength
-  const float sn = K.lambda * fmaf(vdx, ey, -(vdy * ex)); // I x e
+  const float sn = K.lambda * fmaf(vdx, ey, nvdy * ex);   // I x e = lambda (vd x e): exactly 0 for vd == 0
   const float cs = fmaf(ix, ex, iy * ey);                 // I . e
   const float asn = fabsf(sn), acs = fabsf(cs);
   const float m = fminf(asn, acs) * rL;
   const float u = m * m;
-  float p = SFW_ASIN_C7;
-  p = fmaf(p, u, SFW_ASIN_C6);
+  float p = SFW_ASIN_C6;
   p = fmaf(p, u, SFW_ASIN_C5);
   p = fmaf(p, u, SFW_ASIN_C4);
   p = fmaf(p, u, SFW_ASIN_C3);
@@ -204,10 +217,10 @@ __device__ __forceinline__ void pair_force(const SfmConst &K, float ax, float ay
   p = fmaf(p, u, SFW_ASIN_C1);
   p = fmaf(p, u, SFW_ASIN_C0);
   const float th = fold_theta(p * m, asn, acs, cs);
-  const float q = (K.g2 * L2) * (th * th);                // (B theta)^2, B = gamma * interactionLength
-  const float t = -((d2 * rd) * rL) * K.c_d;              // -|diff| / B  (in log2 units)
-  const float e_vel = ex2_approx(fmaf(-K.c_np, q, t));    // exp(-d/B - (n' B theta)^2)
-  const float e_ang = ex2_approx(fmaf(-K.c_n, q, t));     // exp(-d/B - (n  B theta)^2)
+  const float q = L2 * (th * th);                         // (L theta)^2
+  const float t = ((d2 * rd) * rL) * -K.c_d;              // -|diff| / B  (in log2 units)
+  const float e_vel = ex2_approx(fmaf(-K.kq_v, q, t));    // exp(-d/B - (n' B theta)^2)
+  const float e_ang = ex2_approx(fmaf(-K.kq_a, q, t));    // exp(-d/B - (n  B theta)^2)
   const float rLkn = rL * -K.k_soc;
   const float fvn = e_vel * rLkn;                         // force along interactionVector (negative)
   const float fa = signed_angle_term(e_ang * rLkn, sn, cs);
@@ -220,7 +233,8 @@ __device__ __forceinline__ void pair_force(const SfmConst &K, float ax, float ay
   }
 }
 
-// packed version: two (a, b) evaluations at once, one per register half
+// packed version: two (a, b) evaluations at once, one per register half (41 packed FP32x2 operations,
+// 8 MUFU; the rest is per-half compare / select work on the ALU pipe)
 template <bool WITH_MAG>
 __device__ __forceinline__ void pair_force2(const SfmConst &K, f2 ax, f2 ay, f2 avx, f2 avy, f2 bx,
                                             f2 by, f2 bvx, f2 bvy, f2 &fx, f2 &fy, f2 &fmag) {
@@ -229,12 +243,12 @@ __device__ __forceinline__ void pair_force2(const SfmConst &K, f2 ax, f2 ay, f2 
   const f2 d2 = fma2(dx, dx, fma2(dy, dy, eps));
   const f2 rd = rsqrt2(d2);
   const f2 ex = mul2(dx, rd), ey = mul2(dy, rd);
-  const f2 vdx = sub2(avx, bvx), vdy = sub2(avy, bvy);
+  const f2 vdx = sub2(avx, bvx), nvdy = sub2(bvy, avy);
   const f2 lam = bc2(K.lambda);
-  const f2 ix = fma2(lam, vdx, ex), iy = fma2(lam, vdy, ey);
+  const f2 ix = fma2(lam, vdx, ex), iy = fma2(bc2(-K.lambda), nvdy, ey);
   const f2 L2 = fma2(ix, ix, fma2(iy, iy, eps));
   const f2 rL = rsqrt2(L2);
-  const f2 sn = mul2(lam, sub2(mul2(vdx, ey), mul2(vdy, ex)));
+  const f2 sn = mul2(lam, fma2(vdx, ey, mul2(nvdy, ex)));
   const f2 cs = fma2(ix, ex, mul2(iy, ey));
   float sn0, sn1, cs0, cs1;
   un2(sn, sn0, sn1);
@@ -242,8 +256,7 @@ __device__ __forceinline__ void pair_force2(const SfmConst &K, f2 ax, f2 ay, f2 
   const float asn0 = fabsf(sn0), asn1 = fabsf(sn1), acs0 = fabsf(cs0), acs1 = fabsf(cs1);
   const f2 m = mul2(mk2(fminf(asn0, acs0), fminf(asn1, acs1)), rL);
   const f2 u = mul2(m, m);
-  f2 p = bc2(SFW_ASIN_C7);
-  p = fma2(p, u, bc2(SFW_ASIN_C6));
+  f2 p = bc2(SFW_ASIN_C6);
   p = fma2(p, u, bc2(SFW_ASIN_C5));
   p = fma2(p, u, bc2(SFW_ASIN_C4));
   p = fma2(p, u, bc2(SFW_ASIN_C3));
@@ -253,20 +266,20 @@ __device__ __forceinline__ void pair_force2(const SfmConst &K, f2 ax, f2 ay, f2 
   float ph0, ph1;
   un2(mul2(p, m), ph0, ph1);
   const f2 th = mk2(fold_theta(ph0, asn0, acs0, cs0), fold_theta(ph1, asn1, acs1, cs1));
-  const f2 q = mul2(mul2(bc2(K.g2), L2), mul2(th, th));
+  const f2 q = mul2(L2, mul2(th, th));
   const f2 t = mul2(mul2(mul2(d2, rd), rL), bc2(-K.c_d));
   float a0, a1, b0, b1;
-  un2(fma2(bc2(-K.c_np), q, t), a0, a1);
-  un2(fma2(bc2(-K.c_n), q, t), b0, b1);
+  un2(fma2(bc2(-K.kq_v), q, t), a0, a1);
+  un2(fma2(bc2(-K.kq_a), q, t), b0, b1);
   const float ev0 = ex2_approx(a0), ev1 = ex2_approx(a1);
   const float ea0 = ex2_approx(b0), ea1 = ex2_approx(b1);
   const f2 rLkn = mul2(rL, bc2(-K.k_soc));
   const f2 fvn = mul2(mk2(ev0, ev1), rLkn);
   float m0, m1;
   un2(mul2(mk2(ea0, ea1), rLkn), m0, m1);
-  const f2 fa = mk2(signed_angle_term(m0, sn0, cs0), signed_angle_term(m1, sn1, cs1));
-  fx = fma2(fa, iy, mul2(fvn, ix));
-  fy = sub2(mul2(fvn, iy), mul2(fa, ix));
+  const float fa0 = signed_angle_term(m0, sn0, cs0), fa1 = signed_angle_term(m1, sn1, cs1);
+  fx = fma2(mk2(fa0, fa1), iy, mul2(fvn, ix));
+  fy = fma2(mk2(flip_sign(fa0), flip_sign(fa1)), ix, mul2(fvn, iy));
   if (WITH_MAG) {
     const float z0 = (sn0 == 0.0f && cs0 >= 0.0f) ? 0.0f : ea0;
     const float z1 = (sn1 == 0.0f && cs1 >= 0.0f) ? 0.0f : ea1;

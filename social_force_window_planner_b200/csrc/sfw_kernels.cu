@@ -176,7 +176,7 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   mv.free_bits = use_free ? s_free : nullptr;
   mv.fw32 = fw32;
 
-  const SfmConst K = {B.lambda, B.c_d, B.gamma * B.gamma, B.c_np, B.c_n, B.k_soc};
+  const SfmConst K = make_sfm_const(B);
 
   // ---- which trajectory is mine ----------------------------------------------------------------
   const uint32_t n_w = B.n_w;
