@@ -3,6 +3,7 @@
 #include <geometry_msgs/msg/point.hpp>
 namespace visualization_msgs { namespace msg {
 struct Marker {
+  enum { POINTS = 8, ADD = 0 };
   std_msgs::msg::Header header;
   std::string ns;
   int id = 0;

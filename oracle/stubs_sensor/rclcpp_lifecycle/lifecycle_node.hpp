@@ -4,6 +4,7 @@
 namespace rclcpp_lifecycle {
 template <typename T> struct LifecyclePublisher {
   void on_activate() {}
+  void on_deactivate() {}
   void publish(const T &m) { last = m; ++count; }
   T last;
   int count = 0;

@@ -54,12 +54,14 @@ def build_host(force: bool = False) -> str:
     packer) linked against libsfw_b200.so."""
     build(force=False)
     sensor_src = os.path.join(HERE, "host", "sfw_sensor_host.cpp")
+    node_src = os.path.join(HERE, "host", "sfw_node_host.cpp")
     deps = [HOST_SRC, HOST_SRC.replace(".cpp", ".hpp"), sensor_src, sensor_src.replace(".cpp", ".hpp"),
+            node_src, node_src.replace(".cpp", ".hpp"),
             os.path.join(HERE, "..", "include", "sfw_b200.h"), LIB]
     if not force and os.path.exists(HOST_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_LIB) for d in deps):
         return HOST_LIB
     cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wextra",
-           "-o", HOST_LIB, HOST_SRC, sensor_src, "-L" + HERE, "-l:libsfw_b200.so", "-Wl,-rpath,$ORIGIN"]
+           "-o", HOST_LIB, HOST_SRC, sensor_src, node_src, "-L" + HERE, "-l:libsfw_b200.so", "-Wl,-rpath,$ORIGIN"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

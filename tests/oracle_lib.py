@@ -172,6 +172,29 @@ def ref_sensor_run(scan: dict, people: np.ndarray, odom, params=(3.0, 0.35, 2.0,
     return agents, obs[:n.value].copy()
 
 
+REF_NODE_SO = os.path.join(ORACLE_DIR, "_ref", "libsfw_ref_node.so")
+_ref_node = None
+
+
+def have_ref_node() -> bool:
+    return os.path.exists(REF_NODE_SO)
+
+
+from social_force_window_planner_b200.node import NODE_ARGTYPES, node_call  # noqa: E402  (argument layout only)
+
+
+def ref_node_run(params, ext, scene, scan, people, odom, plan, plan_has_tf=False, tf=(0.0, 0.0, 0.0), ticks=1):
+    """The reference's WHOLE plugin (SFWPlannerNode + planner + sensor interface, compiled unmodified) for
+    `ticks` control ticks: (cmd[ticks, 3], status[ticks], poses left in the pruned plan, isGoalReached)."""
+    global _ref_node
+    if _ref_node is None:
+        lib = C.CDLL(REF_NODE_SO)
+        lib.sfw_ref_node_run.restype = C.c_int
+        lib.sfw_ref_node_run.argtypes = NODE_ARGTYPES
+        _ref_node = lib
+    return node_call(_ref_node.sfw_ref_node_run, params, ext, scene, scan, people, odom, plan, plan_has_tf, tf, ticks)
+
+
 def ref_markers(params, scene, linvels, angvels, max_points=128, sfm=None):
     """MarkerArray the reference's findBestAction leaves after one grid tick: (ok, rgba[n,4], npts[n], xyz[n,max,3])."""
     sa = SceneArray([scene])
