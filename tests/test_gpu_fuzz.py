@@ -1,0 +1,56 @@
+"""-m gpu: randomized shapes against the oracle — pedestrian / obstacle counts (incl. odd crowds, the
+64-pedestrian switch between the two kernels), step counts, footprints, group tags, map sizes, robot states.
+Same bar as tests/test_gpu_parity.py."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+import parity
+from social_force_window_planner_b200 import scenes as S
+from social_force_window_planner_b200.scenes import SplitMix64
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_case(seed):
+    rng = SplitMix64(424242 + seed)
+    pick = lambda lo, hi: lo + int(rng.uniform() * (hi - lo + 1))  # noqa: E731
+    n_peds = [0, 1, 2, 3, 7, 12, 19, 20, 33, 63, 64, 65, 66, 97][pick(0, 13)]
+    steps = pick(6, 48) if n_peds < 60 else pick(6, 20)
+    wl = dataclasses.replace(S.WORKLOADS["C0"], n_v=pick(2, 9), n_w=pick(3, 11), steps=steps, n_peds=n_peds,
+                             map_w=pick(100, 260), map_h=pick(100, 260), ped_r_max=5.5 if n_peds > 30 else None,
+                             ped_sep=0.5 if n_peds > 30 else 0.8)
+    fp = None
+    k = pick(0, 3)
+    if k == 1:
+        fp = np.zeros((0, 2))
+    elif k == 2:
+        fp = np.array([[0.32, 0.22], [-0.28, 0.22], [-0.28, -0.22], [0.32, -0.22]])
+    elif k == 3:
+        fp = S.circle_footprint(rng.uniform(0.2, 0.5), pick(5, 24))
+    sc = S.make_scene(wl, seed, n_obstacles=pick(0, 48), footprint=fp, hazards=rng.uniform() < 0.5,
+                      robot_xy=(rng.uniform(-50, 50), rng.uniform(-50, 50)) if rng.uniform() < 0.3 else (0.0, 0.0),
+                      robot_theta=rng.uniform(-3.1, 3.1))
+    # group tags on some pedestrians (ids 0..2; lone tags stay inert), a few without a goal
+    for j in range(n_peds):
+        u = rng.uniform()
+        if u < 0.35:
+            sc.peds[j]["group_id"] = pick(0, 2)
+        if rng.uniform() < 0.1:
+            sc.peds[j]["has_goal"] = 0
+    p = wl.params()
+    p.max_trans_acc = rng.uniform(0.2, 2.0)
+    p.max_rot_acc = rng.uniform(0.2, 2.0)
+    p.robot_radius = float(np.float32(rng.uniform(0.25, 0.45)))
+    lin, ang = wl.sample_arrays(max_vel_x=rng.uniform(0.4, 1.0), max_vel_th=rng.uniform(0.3, 1.2))
+    p.max_vel_x = float(lin[-1])
+    return wl, p, sc, lin, ang
+
+
+@pytest.mark.parametrize("seed", range(28))
+def test_random_scene_vs_oracle(scorer, seed):
+    wl, p, sc, lin, ang = _random_case(seed)
+    costs, best = scorer.score(p, [sc], lin, ang)
+    st = parity.compare(p, sc, lin, ang, costs[0], best[0], max_near_frac=1.0)
+    print(seed, wl.n_peds, "peds", len(sc.obstacles), "obst", wl.steps, "steps", scorer.last_kernel, st)
