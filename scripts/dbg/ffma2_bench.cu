@@ -84,6 +84,20 @@ template <int MODE> __global__ void k(float *out, int iters, float a, float b) {
       for (int i = 0; i < NX; ++i) {
         asm volatile("xor.b32 %0, %0, %1;" : "+r"(xr[i]) : "r"(it));
       }
+    } else if (MODE >= 13 && MODE <= 16) {  // 8 MUFU of one kind: 13 rsqrt, 14 sqrt, 15 rcp, 16 rsqrt+ex2 alternating
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float y;
+        if (MODE == 13 || (MODE == 16 && (i & 1)))
+          asm volatile("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(acc[i]));
+        else if (MODE == 14)
+          asm volatile("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(acc[i]));
+        else if (MODE == 15)
+          asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(acc[i]));
+        else
+          asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(acc[i]));
+        acc[i] = y;
+      }
     } else if (MODE == 3) {  // mix: 1 MUFU per 4 FFMA2
 #pragma unroll
       for (int i = 0; i < 8; ++i) p[i] = fma2(p[i], pa, pb);
@@ -140,5 +154,9 @@ int main() {
   run<10>("8 FFMA2 + 16 XOR", 32);
   run<11>("16 XOR", 16);
   run<12>("16 FFMA + 16 XOR", 32);
+  run<13>("MUFU.RSQ (8 per iter)", 8);
+  run<14>("MUFU.SQRT (8 per iter)", 8);
+  run<15>("MUFU.RCP (8 per iter)", 8);
+  run<16>("MUFU.RSQ/EX2 alternating (8)", 8);
   return 0;
 }
