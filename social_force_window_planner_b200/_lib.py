@@ -11,7 +11,7 @@ import os
 from ._abi import SfwBest, SfwLaserScan, SfwLimits, SfwParams, SfwScene, SfwSfmParams
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsfw_b200.so")
+LIB_PATH = os.environ.get("SFW_B200_LIB") or os.path.join(HERE, "libsfw_b200.so")  # override: kernel experiments
 
 # every symbol include/sfw_b200.h declares
 EXPORTS = [

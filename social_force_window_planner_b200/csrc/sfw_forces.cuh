@@ -291,24 +291,33 @@ __device__ __forceinline__ void pair_force2(const SfmConst &K, f2 ax, f2 ay, f2 
 // stored pre-multiplied by c_obs = log2(e)/sigma, and so is the query point: then |p'-o'| is the
 // exponent in log2 units and the unit vector is unchanged.  The list is padded to an even count
 // with a point 1e15 away, whose term is exactly 0 (ex2 underflows).
-// (a) two query points (a pedestrian pair) against every obstacle
+// one obstacle point against the two pedestrians of a pair
+__device__ __forceinline__ void obstacle_term2(float2 p, f2 qx, f2 qy, f2 &ax, f2 &ay) {
+  const f2 dx = sub2(qx, bc2(p.x)), dy = sub2(qy, bc2(p.y));
+  const f2 d2 = fma2(dx, dx, fma2(dy, dy, bc2(1e-30f)));
+  const f2 rd = rsqrt2(d2);
+  float d0, d1;
+  un2(mul2(d2, rd), d0, d1);
+  const f2 e = mul2(mk2(ex2_approx(-d0), ex2_approx(-d1)), rd);
+  ax = fma2(e, dx, ax);
+  ay = fma2(e, dy, ay);
+}
+
+// (a) two query points (a pedestrian pair) against every obstacle, 8 points per trip (the loop is
+// instruction bound: a software exponential on the FMA pipe for some of the points made it slower,
+// DESIGN.md 4.4)
 __device__ __forceinline__ void obstacle_sum2(const float2 *__restrict__ obs, int M, float c_obs, f2 px,
                                               f2 py, f2 &sx, f2 &sy) {
   f2 ax = bc2(0.f), ay = bc2(0.f);
-  const f2 eps = bc2(1e-30f);
   const f2 qx = mul2(px, bc2(c_obs)), qy = mul2(py, bc2(c_obs));
-#pragma unroll 4
-  for (int o = 0; o < M; ++o) {
-    const float2 p = obs[o];
-    const f2 dx = sub2(qx, bc2(p.x)), dy = sub2(qy, bc2(p.y));
-    const f2 d2 = fma2(dx, dx, fma2(dy, dy, eps));
-    const f2 rd = rsqrt2(d2);
-    float d0, d1;
-    un2(mul2(d2, rd), d0, d1);
-    const f2 e = mul2(mk2(ex2_approx(-d0), ex2_approx(-d1)), rd);
-    ax = fma2(e, dx, ax);
-    ay = fma2(e, dy, ay);
+  int o = 0;
+  for (; o + 8 <= M; o += 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      obstacle_term2(obs[o + i], qx, qy, ax, ay);
   }
+  for (; o < M; ++o)
+    obstacle_term2(obs[o], qx, qy, ax, ay);
   sx = ax;
   sy = ay;
 }
