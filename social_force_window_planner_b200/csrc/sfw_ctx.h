@@ -41,7 +41,8 @@ struct sfw_ctx {
 
   SfwArena in;   // packed inputs
   SfwArena out;  // best | costs | npts | blockbest | counters
-  SfwArena sensor_in, sensor_out; // sfw_laser_obstacles staging
+  SfwArena sensor_in, sensor_out; // sfw_laser_obstacles / sfw_marker_points staging
+  bool laser_attr_set = false;
   double *d_points = nullptr;
   double *h_points = nullptr;
   uint32_t points_cap = 0;

@@ -185,10 +185,9 @@ extern "C" int sfw_laser_obstacles(sfw_ctx *c, const SfwLaserScan *scans, uint32
     pp += L.n_people;
   }
   SFW_CK(c, cudaMemcpyAsync(c->sensor_in.dev, h, in_bytes, cudaMemcpyHostToDevice, c->stream));
-  static bool attr_done = false;
-  if (!attr_done) {
+  if (!c->laser_attr_set) { // per context: a process may drive several devices
     SFW_CK(c, cudaFuncSetAttribute(sfw_laser_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
+    c->laser_attr_set = true;
   }
   uint8_t *dv = c->sensor_in.dev, *dout = c->sensor_out.dev;
   SFW_CK(c, cudaMemsetAsync(dout + o_fill, 0, 4, c->stream));

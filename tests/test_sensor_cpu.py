@@ -6,6 +6,7 @@ import oracle_lib as ol
 import sensor_cases as SC
 
 
+@np.errstate(invalid="ignore", over="ignore")
 def _numpy_laser(scan, max_dist=3.0, person_radius=0.35):
     r = np.asarray(scan["ranges"], dtype=np.float32)
     n = len(r)
