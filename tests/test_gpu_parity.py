@@ -258,3 +258,92 @@ def test_crowd_kernel_with_groups(scorer):
     costs0, _ = scorer.score(p, [sc], lin, ang)
     assert not np.array_equal(costs0, costs), "group tags must change the result"
     print(st)
+
+
+# ---- BASELINE.json configs[2..4] at FULL size: size-independent properties + oracle spot checks -------
+def _spot_check(p, sc, lin, ang, costs, picks):
+    """A handful of trajectories of a big grid against the oracle's single-trajectory scorer."""
+    import ctypes as C
+    import oracle_lib as ol
+    from social_force_window_planner_b200._abi import SceneArray
+    sa = SceneArray([sc])
+    n_w = len(ang)
+    for idx in picks:
+        v, w = lin[idx // n_w], ang[idx % n_w]
+        if v == 0.0 and w == 0.0:
+            assert costs[idx] == -2.0
+            continue
+        mg = ol.SfwOracleMargins()
+        c = ol.oracle().sfw_oracle_score_trajectory(C.byref(p), None, sa.ptr(0), v, 0.0, w, p.max_trans_acc, 0.0,
+                                                    p.max_rot_acc, None, 0, None, C.byref(mg))
+        clear = mg.goal > parity.GOAL_MARGIN and mg.collision > parity.COLLISION_MARGIN and mg.theta > parity.THETA_MARGIN
+        if c < 0:
+            assert costs[idx] < 0 or not clear, (idx, c, costs[idx])
+        else:
+            assert costs[idx] >= 0 or not clear, (idx, c, costs[idx])
+            if costs[idx] >= 0:
+                assert abs(costs[idx] - c) <= (parity.RTOL if clear else parity.NEAR_RTOL) * abs(c), (idx, c, costs[idx])
+
+
+def _host_argmin(costs, lin, ang):
+    import ctypes as C
+    import oracle_lib as ol
+    from social_force_window_planner_b200._abi import SfwBest
+    sb = SfwBest()
+    dp = C.POINTER(C.c_double)
+    c64 = np.ascontiguousarray(costs, dtype=np.float64)
+    ol.oracle().sfw_oracle_argmin(c64.ctypes.data_as(dp), lin.ctypes.data_as(dp), len(lin), ang.ctypes.data_as(dp),
+                                  len(ang), C.byref(sb))
+    return sb.valid, sb.index
+
+
+def test_full_size_c4_fine_sweep(scorer):
+    """configs[4]: 1024x1024 samples, 32 steps, 10 pedestrians, 800x800 costmap."""
+    wl = S.WORKLOADS["C4"]
+    sc = S.make_scene(wl, 0)
+    p = wl.params()
+    lin, ang = wl.sample_arrays()
+    costs, best = scorer.score(p, [sc], lin, ang)
+    assert costs.shape == (1, 1024 * 1024)
+    assert _host_argmin(costs[0], lin, ang) == (int(best[0]["valid"]), int(best[0]["index"]))
+    ri, ci = np.arange(3, wl.n_v, 97), np.arange(5, wl.n_w, 89)
+    sub, sb = scorer.score(p, [sc], lin[ri], np.ascontiguousarray(ang[ci]))
+    assert np.array_equal(sub[0].reshape(len(ri), len(ci)), costs[0].reshape(wl.n_v, wl.n_w)[np.ix_(ri, ci)])
+    parity.compare(p, sc, lin[ri], np.ascontiguousarray(ang[ci]), sub[0], sb[0])
+
+
+def test_full_size_c3_scene_batch(scorer):
+    """configs[3] at one GPU's share of the 8-GPU run: 512 independent scenes, 64x64 samples, 32 steps, 10 peds.
+    Batch results must equal single-scene calls bit for bit (scenes are independent), a few against the oracle."""
+    wl = S.WORKLOADS["C3"]
+    scs = S.make_scenes(wl, 512)
+    p = wl.params()
+    lin, ang = wl.sample_arrays()
+    costs, best = scorer.score(p, scs, lin, ang)
+    assert costs.shape == (512, 4096)
+    for k in (0, 137, 511):
+        c1, b1 = scorer.score(p, [scs[k]], lin, ang)
+        assert np.array_equal(c1[0], costs[k]) and b1[0] == best[k]
+        assert _host_argmin(costs[k], lin, ang) == (int(best[k]["valid"]), int(best[k]["index"]))
+    _spot_check(p, scs[300], lin, ang, costs[300], [0, 1, 63, 64, 2047, 2048 + 31, 4095])
+    parity.compare(p, scs[77], lin[::9], np.ascontiguousarray(ang[::7]),
+                   costs[77].reshape(64, 64)[::9, ::7].reshape(-1),
+                   scorer.score(p, [scs[77]], lin[::9], np.ascontiguousarray(ang[::7]))[1][0])
+
+
+def test_full_size_c2_dense_crowd_slab(scorer):
+    """configs[2] (128x128 samples, 128 steps, 500 pedestrians): two linvel rows of the full grid through the
+    row-slab interface (the whole grid takes 0.45 s of GPU time and minutes of oracle time), trajectories
+    spot-checked against the oracle; rows outside the slab stay SKIPPED."""
+    wl = S.WORKLOADS["C2"]
+    sc = S.make_scene(wl, 0)
+    p = wl.params()
+    lin, ang = wl.sample_arrays()
+    scorer.upload(p, [sc], lin, ang)
+    scorer.set_row_slab(40, 42)
+    scorer.run()
+    costs, best = scorer.download()
+    assert scorer.last_kernel == "sfw_score_crowd"
+    c = costs[0].reshape(128, 128)
+    assert (c[:40] == -2.0).all() and (c[42:] == -2.0).all() and (c[40:42] != -2.0).all()
+    _spot_check(p, sc, lin, ang, costs[0], [40 * 128 + 3, 40 * 128 + 64, 41 * 128 + 100, 41 * 128 + 127])
