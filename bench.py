@@ -198,7 +198,7 @@ def workload_config(wl, n_gpus, l2):
     return {"workload": f"{wl.name}: {wl.n_v}x{wl.n_w} (v,w) samples, {wl.steps} steps, {wl.n_peds} pedestrians, "
                         f"{wl.map_w}x{wl.map_h} costmap, {wl.n_obstacles} obstacle points, 16-gon footprint",
             "scenes_per_gpu": 1, "scenes_total": n_gpus, "trajectories_per_step": wl.samples * n_gpus,
-            "parallelism": f"scene-batch sharding x{n_gpus} + NCCL all-gather of winners" if n_gpus > 1 else "single GPU",
+            "parallelism": f"scene-batch sharding x{n_gpus} + winner exchange" if n_gpus > 1 else "single GPU",
             "seeds": "1000 + rank", "l2": l2}
 
 
@@ -214,6 +214,9 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=48, help="cpu_baseline leg: sub-grid rows")
     ap.add_argument("--cpu-cols", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: winners exchanged by the scorer's own epilogue over NVLink peer memory (fused) "
+                         "or by an NCCL all-gather after the kernel (nccl)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -268,9 +271,35 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # ---- winner exchange: fused into the kernel epilogue (peer stores over NVLink) unless --exchange nccl ----
+    exchange = "none"
+    if world > 1:
+        exchange = args.exchange
+        if exchange == "fused":
+            ok = True
+            try:
+                handles = [None] * world
+                dist.all_gather_object(handles, scorer.exchange_export(1))
+                scorer.exchange_connect(rank, world, handles)
+            except Exception as e:  # e.g. cudaIpc unavailable in a restricted container
+                sys.stderr.write(f"[rank {rank}] fused exchange unavailable ({e}); using NCCL all-gather\n")
+                ok = False
+            flag = torch.tensor([1 if ok else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                if ok:
+                    raise SystemExit("bench.py: fused exchange connected on some ranks only")
+                exchange = "nccl"
+        dist.barrier()
+
     def gather_winners():
-        """NCCL all-gather of the per-scene winner records (32 B per scene) on the scorer's stream."""
+        """Every rank learns every scene's winner: the records were already stored into all ranks' gather
+        buffers by the scorer's epilogue (fused; only a device-side arrival wait is enqueued here), or an
+        NCCL all-gather of the 32-byte records on the scorer's stream."""
         if world == 1:
+            return None
+        if exchange == "fused":
+            scorer.exchange_sync()
             return None
         import ctypes as C
         ptr = scorer._lib.sfw_device_best(scorer._ctx)
@@ -375,6 +404,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_s / args.steps * 1e3, "api": "sfw_score_batch (C ABI, host buffers)"},
             "gpu_launches": int(launches),
+            "exchange": {"fused": "winner records stored into every rank's gather buffer over NVLink by the scorer's "
+                                  "epilogue; device-side arrival wait (1 tiny kernel per tick)",
+                         "nccl": "NCCL all-gather of the 32-byte winner records after the kernel",
+                         "none": "single GPU"}[exchange],
             "kernel": kernel_name, "kernel_ms": k_ms, "wall_s_timed_region": t_wall,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,

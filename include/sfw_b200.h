@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SFW_ABI_VERSION 2
+#define SFW_ABI_VERSION 3
 
 /* status codes */
 #define SFW_OK 0
@@ -230,6 +230,24 @@ typedef struct SfwLaserScan {
 int sfw_laser_obstacles(sfw_ctx *ctx, const SfwLaserScan *scans, uint32_t n_scans, float max_obstacle_dist,
                         float person_radius, double *points_xy_out, uint32_t max_points_per_scan,
                         uint32_t *n_points_out);
+
+/* ---- multi-GPU: winner exchange fused into the scorer's epilogue -------------------------------
+ * One process per GPU, every rank scoring its own scenes (BASELINE configs[3]); the only cross-rank step is
+ * that every rank learns every scene's winner.  After sfw_exchange_connect, each sfw_run stores its SfwBest
+ * records directly into every rank's gather buffer over NVLink (peer mappings of cudaIpc handles) from the
+ * kernel that reduces them; no collective follows the kernel.
+ *   sfw_exchange_export   allocate this rank's gather buffer (max_scenes per rank), write its 64-byte
+ *                         cudaIpcMemHandle_t to handle_out; the caller ships the handles to all ranks
+ *   sfw_exchange_connect  handles = world x 64 bytes in rank order (own slot ignored); world <= 8;
+ *                         every rank must stage the SAME number of scenes per tick from here on
+ *   sfw_exchange_sync     enqueue a device-side wait on the context stream until every rank's records of the
+ *                         latest sfw_run have arrived (asynchronous for the host)
+ *   sfw_exchange_fetch    sync + copy the gathered records to all_best_out[world][n_scenes] (rank major) */
+int sfw_exchange_export(sfw_ctx *ctx, uint32_t max_scenes, void *handle_out);
+int sfw_exchange_connect(sfw_ctx *ctx, uint32_t rank, uint32_t world, const void *handles);
+int sfw_exchange_sync(sfw_ctx *ctx);
+int sfw_exchange_fetch(sfw_ctx *ctx, SfwBest *all_best_out);
+const void *sfw_exchange_device_buffer(sfw_ctx *ctx); /* device [world][max_scenes] SfwBest of the latest run */
 
 /* ---- introspection (benchmark / interop) ---------------------------------------------------- */
 void *sfw_stream(sfw_ctx *ctx);                 /* cudaStream_t the context launches on */

@@ -19,7 +19,8 @@ EXPORTS = [
     "sfw_default_sfm_params", "sfw_score", "sfw_score_batch", "sfw_upload", "sfw_run",
     "sfw_download", "sfw_sync", "sfw_set_row_slab", "sfw_trajectory_points", "sfw_stream",
     "sfw_device_costs", "sfw_device_best", "sfw_kernel_launches", "sfw_algorithmic_bytes",
-    "sfw_last_kernel", "sfw_h2d_bytes", "sfw_d2h_bytes", "sfw_laser_obstacles", "sfw_marker_points",
+    "sfw_last_kernel", "sfw_h2d_bytes", "sfw_d2h_bytes", "sfw_laser_obstacles", "sfw_marker_points", "sfw_exchange_export", "sfw_exchange_connect",
+    "sfw_exchange_sync", "sfw_exchange_fetch", "sfw_exchange_device_buffer",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -82,6 +83,16 @@ def load() -> C.CDLL:
     lib.sfw_marker_points.restype = C.c_int
     lib.sfw_marker_points.argtypes = [_ctx, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _dp, C.c_uint32,
                                       C.POINTER(C.c_uint16)]
+    lib.sfw_exchange_export.restype = C.c_int
+    lib.sfw_exchange_export.argtypes = [_ctx, C.c_uint32, C.c_void_p]
+    lib.sfw_exchange_connect.restype = C.c_int
+    lib.sfw_exchange_connect.argtypes = [_ctx, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.sfw_exchange_sync.restype = C.c_int
+    lib.sfw_exchange_sync.argtypes = [_ctx]
+    lib.sfw_exchange_fetch.restype = C.c_int
+    lib.sfw_exchange_fetch.argtypes = [_ctx, C.POINTER(SfwBest)]
+    lib.sfw_exchange_device_buffer.restype = C.c_void_p
+    lib.sfw_exchange_device_buffer.argtypes = [_ctx]
     lib.sfw_last_kernel.restype = C.c_char_p
     lib.sfw_last_kernel.argtypes = [_ctx]
     return lib

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsfw_b200.so")
-SOURCES = ["sfw_kernels.cu", "sfw_crowd.cu", "sfw_abi.cu", "sfw_sensor.cu"]
+SOURCES = ["sfw_kernels.cu", "sfw_crowd.cu", "sfw_abi.cu", "sfw_sensor.cu", "sfw_exchange.cu"]
 HEADERS = ["sfw_dev.h", "sfw_kernels.h", "sfw_forces.cuh", "sfw_ctx.h", os.path.join("..", "..", "include", "sfw_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

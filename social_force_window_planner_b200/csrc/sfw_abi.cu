@@ -301,6 +301,13 @@ int sfw_destroy(sfw_ctx *c) {
     if (a->dev)
       cudaFree(a->dev);
   }
+  for (uint32_t q = 0; q < c->xchg.world && c->xchg.connected; ++q)
+    if (q != c->xchg.rank && c->xchg.peer[q])
+      cudaIpcCloseMemHandle(c->xchg.peer[q]);
+  if (c->xchg.local)
+    cudaFree(c->xchg.local);
+  if (c->xchg.host)
+    cudaFreeHost(c->xchg.host);
   if (c->d_points)
     cudaFree(c->d_points);
   if (c->h_points)
@@ -763,6 +770,23 @@ int sfw_run(sfw_ctx *c) {
       }
     }
     CK(c, cudaMemsetAsync(B.npts, 0, n * 2, c->stream));
+  }
+  // fused winner exchange: this launch writes epoch parity `slot` of every rank's gather buffer
+  memset(&B.xchg, 0, sizeof(B.xchg));
+  if (c->xchg.connected && re > rb) {
+    if (B.n_scenes > c->xchg.max_scenes)
+      return fail(c, SFW_ERR_ARG, "%u scenes staged but the exchange buffer holds %u", B.n_scenes, c->xchg.max_scenes);
+    for (uint32_t q = 0; q < c->xchg.world; ++q) {
+      B.xchg.peer_best[q] = reinterpret_cast<SfwBest *>(c->xchg.peer[q]);
+      B.xchg.peer_arrived[q] = reinterpret_cast<unsigned int *>((uint8_t *)c->xchg.peer[q] + c->xchg.off_arrived);
+    }
+    B.xchg.rank = c->xchg.rank;
+    B.xchg.world = c->xchg.world;
+    B.xchg.max_scenes = c->xchg.max_scenes;
+    B.xchg.enabled = 1;
+    B.xchg.slot = (uint32_t)(c->xchg.epoch & 1u);
+    c->xchg.epoch += 1;
+    c->xchg.expected += B.n_scenes; // every rank stages the same number of scenes per tick
   }
   if (re > rb && c->plan.crowd) {
     CK(c, sfw_launch_crowd(B, reinterpret_cast<unsigned int *>(c->out.dev + c->off_work), c->plan.grid,

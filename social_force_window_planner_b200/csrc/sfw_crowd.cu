@@ -573,6 +573,8 @@ __global__ void __launch_bounds__(256) sfw_argmin_kernel(const __grid_constant__
       r.v = r.valid ? B.linvels[bi / n_w] : 0.0;
       r.w = r.valid ? B.angvels[bi % n_w] : 0.0;
       B.best[scene] = r;
+      if (B.xchg.enabled)
+        export_best(B.xchg, scene, r);
     }
   }
 }

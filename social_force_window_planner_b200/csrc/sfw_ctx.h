@@ -43,6 +43,18 @@ struct sfw_ctx {
   SfwArena out;  // best | costs | npts | blockbest | counters
   SfwArena sensor_in, sensor_out; // sfw_laser_obstacles / sfw_marker_points staging
   bool laser_attr_set = false;
+
+  // fused multi-GPU winner exchange (csrc/sfw_exchange.cu)
+  struct {
+    bool exported = false, connected = false;
+    uint32_t rank = 0, world = 1, max_scenes = 0;
+    uint8_t *local = nullptr; // [2][world_max][max_scenes] SfwBest | arrived[SFW_MAX_RANKS]
+    size_t bytes = 0, off_arrived = 0;
+    void *peer[SFW_MAX_RANKS] = {};
+    uint64_t epoch = 0;     // launches exported so far
+    uint64_t expected = 0;  // records every rank must have delivered by now
+    uint8_t *host = nullptr; // pinned landing buffer of sfw_exchange_fetch
+  } xchg;
   double *d_points = nullptr;
   double *h_points = nullptr;
   uint32_t points_cap = 0;

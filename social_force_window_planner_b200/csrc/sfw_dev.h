@@ -52,6 +52,18 @@ struct SfwBlockBest {
   uint32_t index;
 };
 
+#define SFW_MAX_RANKS 8
+// Multi-GPU winner exchange fused into the scorer's epilogue (csrc/sfw_exchange.cu): every rank owns a gather
+// buffer [2 epochs][world][max_scenes] of SfwBest plus one arrival counter per source rank; the block that
+// reduces a scene's winner stores the record straight into EVERY rank's buffer over NVLink (peer mappings of
+// cudaIpc handles) and then bumps that rank's counter with a system-scope release.
+struct SfwExchangeDev {
+  SfwBest *peer_best[SFW_MAX_RANKS];         // peer q's gather buffer (q == rank: the local one)
+  unsigned int *peer_arrived[SFW_MAX_RANKS]; // peer q's arrival counters [world]
+  uint32_t rank, world, max_scenes, enabled;
+  uint32_t slot, pad0;                       // epoch parity of this launch
+};
+
 struct SfwBatchDev {
   const SfwSceneDev *scenes;
   // pedestrians are stored as PAIRS (2k, 2k+1), one float4 per pair and quantity, so that the two
@@ -98,6 +110,7 @@ struct SfwBatchDev {
   float dtf;        // (float)dt
   float k_gaze, k_coh, k_rep; // forceFactorGroupGaze / Coherence / Repulsion
   float pad2;
+  SfwExchangeDev xchg;
 };
 
 #endif

@@ -609,6 +609,21 @@ __device__ __forceinline__ bool better(float ca, uint32_t ia, float cb, uint32_t
   return ia > ib;
 }
 
+// Fused winner exchange: store one scene's record into every rank's gather buffer (peer memory over NVLink),
+// make the stores visible system-wide, then signal each rank's arrival counter.  Called by ONE thread.
+__device__ __forceinline__ void export_best(const SfwExchangeDev &X, uint32_t scene, const SfwBest &r) {
+  const int4 lo = reinterpret_cast<const int4 *>(&r)[0], hi = reinterpret_cast<const int4 *>(&r)[1];
+  const size_t at = ((size_t)X.slot * X.world + X.rank) * X.max_scenes + scene;
+  for (uint32_t q = 0; q < X.world; ++q) {
+    int4 *dst = reinterpret_cast<int4 *>(X.peer_best[q] + at);
+    dst[0] = lo;
+    dst[1] = hi;
+  }
+  __threadfence_system();
+  for (uint32_t q = 0; q < X.world; ++q)
+    atomicAdd_system(X.peer_arrived[q] + X.rank, 1u);
+}
+
 // A cost can only become "best" if 0 <= cost <= 10000; == 10000 needs linvel > 0 because the
 // initial best is (10000, xv = 0, thetav = 0) (sfw_planner.cpp:338-344,394-407).
 __device__ __forceinline__ bool eligible(float c, double linvel) {

@@ -515,6 +515,8 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
         r.w = r.valid ? B.angvels[bi % n_w] : 0.0;
         B.best[scene] = r;
         B.counters[scene] = 0u; // ready for the next launch
+        if (B.xchg.enabled)
+          export_best(B.xchg, scene, r);
       }
     }
   }

@@ -119,6 +119,30 @@ class Scorer:
                                                 max_points, n.ctypes.data_as(C.POINTER(C.c_uint16))))
         return xyz, n
 
+    # -- multi-GPU: winner exchange fused into the scorer's epilogue -----------------------------------
+    def exchange_export(self, max_scenes: int) -> bytes:
+        """Allocate this rank's gather buffer; returns its 64-byte cudaIpc handle (ship it to every rank)."""
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.sfw_exchange_export(self._ctx, max_scenes, buf))
+        return buf.raw
+
+    def exchange_connect(self, rank: int, world: int, handles):
+        """``handles``: the ``world`` exported handles in rank order."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        self._xchg_world = world
+        self._check(self._lib.sfw_exchange_connect(self._ctx, rank, world, C.c_char_p(blob)))
+
+    def exchange_sync(self):
+        """Device-side wait (enqueued on the context stream) for every rank's records of the latest run."""
+        self._check(self._lib.sfw_exchange_sync(self._ctx))
+
+    def exchange_fetch(self):
+        """Gathered winners of the latest run: BEST_DTYPE[world, n_scenes] (rank major)."""
+        out = np.zeros((self._xchg_world, self.n_scenes), dtype=BEST_DTYPE)
+        self._check(self._lib.sfw_exchange_fetch(self._ctx, out.ctypes.data_as(C.POINTER(SfwBest))))
+        return out
+
     # -- the step before the path: laser scans -> obstacle points ----------------------------------
     def laser_obstacles(self, scans, max_obstacle_dist: float = 3.0, person_radius: float = 0.35):
         """``sfw_laser_obstacles`` (SFMSensorInterface::laserCb, reference src/sensor_interface.cpp:103-229).
