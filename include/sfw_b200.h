@@ -188,6 +188,18 @@ int sfw_run(sfw_ctx *ctx);             /* launch the scorer on the staged scenes
 int sfw_download(sfw_ctx *ctx, float *costs_out, SfwBest *best_out); /* D2H + stream sync */
 int sfw_sync(sfw_ctx *ctx);            /* cudaStreamSynchronize on the context stream */
 
+/* Kernel selection.  SFW_POLICY_AUTO (default): crowds of more than 64 pedestrians use the block-per-
+ * trajectory kernel, smaller ones the thread-per-trajectory kernel — except SMALL GRIDS, which are latency
+ * bound there (a tick costs what one warp costs) and go to the block-per-trajectory kernel while that takes
+ * few waves (a 5 x 9 tick with 20 pedestrians: 0.23 ms instead of 0.90 ms).  The two kernels evaluate the same
+ * model with different summation orders (costs agree to ~1e-6 relative), so callers that need bit-identical
+ * cost vectors whatever the batch size or rank count pin SFW_POLICY_THROUGHPUT (never the small-grid switch);
+ * SFW_POLICY_LATENCY always takes the block-per-trajectory kernel.  Applies from the next sfw_upload. */
+#define SFW_POLICY_AUTO 0
+#define SFW_POLICY_THROUGHPUT 1
+#define SFW_POLICY_LATENCY 2
+int sfw_set_policy(sfw_ctx *ctx, int policy);
+
 /* Restrict the next sfw_run calls to linvel rows [row_begin, row_end) of every staged scene
  * (multi-GPU sharding of a single scene across ranks: each rank scores a slab and the winners
  * are all-gathered by the caller).  Rows outside the slab get SFW_COST_SKIPPED. */

@@ -110,8 +110,10 @@ const SfwSfmParams kDefaultSfm = {2.0, 10.0, 0.2, 2.1, 3.0, 2.0, 1.0, 2.0, 0.35,
 // Choose block size / tiling for the thread-per-trajectory kernel: maximise resident threads per
 // SM under the shared-memory and register limits, then shrink the block so a single-wave launch
 // is spread evenly over all SMs.
+// family: -1 = choose the kernel family here; 0 / 1 = keep thread-per-trajectory / block-per-trajectory (a row
+// slab must be scored by the kernel its full grid was planned for, so that sharding never changes a bit).
 int make_plan(sfw_ctx *c, uint32_t n_scenes, uint32_t samples, uint32_t P, uint32_t M, uint32_t F,
-              uint32_t win_wp, uint32_t win_h, int steps) {
+              uint32_t win_wp, uint32_t win_h, int steps, int family = -1) {
   Plan &pl = c->plan;
   if (pl.valid && pl.n_scenes == n_scenes && pl.samples == samples && pl.maxP == P && pl.maxM == M &&
       pl.maxF == F && pl.win_wp == win_wp && pl.win_h == win_h && pl.steps == steps)
@@ -125,8 +127,26 @@ int make_plan(sfw_ctx *c, uint32_t n_scenes, uint32_t samples, uint32_t P, uint3
   bool try_small = P <= SFW_MAX_PEDS_SMALL;
   if (try_small && sfw_small_smem_bytes(win_wp, win_h, P, M, F, 128) > max_dyn)
     try_small = false; // fewer than 4 warps per SM would fit
+  if (family == 1 || (family < 0 && c->policy == SFW_POLICY_LATENCY))
+    try_small = false;
+  const size_t crowd_smem = sfw_crowd_smem_bytes(P, M, F, (uint32_t)steps);
+  if (try_small && family < 0 && c->policy == SFW_POLICY_AUTO && P >= 1 && crowd_smem <= max_dyn) {
+    // Small grids are latency bound in the thread-per-trajectory kernel: one thread walks every pair of a
+    // trajectory, so a tick costs what ONE warp costs (0.9 ms for 20 pedestrians / 40 steps) however few
+    // trajectories there are.  The block-per-trajectory kernel spreads a trajectory's pairs over threads and
+    // runs one block per trajectory: a wave of it takes steps x ~(1 + 0.06 P) us.  Measured crossover
+    // (scripts/latency_probe.py): it wins while its wave count stays below ~0.3 P.
+    int k = 0;
+    CK(c, sfw_crowd_prepare(crowd_smem, &k));
+    if (k > 0) {
+      const uint64_t total = (uint64_t)n_scenes * samples;
+      const uint64_t waves = (total + (uint64_t)c->sm_count * k - 1) / ((uint64_t)c->sm_count * k);
+      if ((double)waves <= 0.3 * (double)P)
+        try_small = false;
+    }
+  }
   if (!try_small) {
-    const size_t smem = sfw_crowd_smem_bytes(P, M, F, (uint32_t)steps);
+    const size_t smem = crowd_smem;
     int k = 0;
     if (smem > max_dyn)
       return fail(c, SFW_ERR_UNSUPPORTED,
@@ -717,6 +737,17 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   return SFW_OK;
 }
 
+int sfw_set_policy(sfw_ctx *c, int policy) {
+  if (!c)
+    return SFW_ERR_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (policy < SFW_POLICY_AUTO || policy > SFW_POLICY_LATENCY)
+    return fail(c, SFW_ERR_ARG, "sfw_set_policy: unknown policy %d", policy);
+  c->policy = policy;
+  c->plan.valid = false;
+  return SFW_OK;
+}
+
 int sfw_set_row_slab(sfw_ctx *c, uint32_t row_begin, uint32_t row_end) {
   if (!c)
     return SFW_ERR_ARG;
@@ -749,7 +780,7 @@ int sfw_run(sfw_ctx *c) {
     Plan saved = c->plan;
     c->plan.valid = false;
     int rc = make_plan(c, B.n_scenes, std::max(samples, 1u), saved.maxP, saved.maxM, saved.maxF,
-                       saved.win_wp, saved.win_h, saved.steps);
+                       saved.win_wp, saved.win_h, saved.steps, saved.crowd ? 1 : 0);
     if (rc != SFW_OK)
       return rc;
     B.tiles_per_scene = c->plan.tiles;

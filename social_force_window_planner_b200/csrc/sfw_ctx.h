@@ -43,6 +43,7 @@ struct sfw_ctx {
   SfwArena out;  // best | costs | npts | blockbest | counters
   SfwArena sensor_in, sensor_out; // sfw_laser_obstacles / sfw_marker_points staging
   bool laser_attr_set = false;
+  int policy = 0; // SFW_POLICY_*
 
   // fused multi-GPU winner exchange (csrc/sfw_exchange.cu)
   struct {

@@ -64,6 +64,12 @@ class Scorer:
         self.n_scenes = len(sa)
         self.n_samples = len(lin) * len(ang)
 
+    POLICY_AUTO, POLICY_THROUGHPUT, POLICY_LATENCY = 0, 1, 2
+
+    def set_policy(self, policy: int):
+        """Kernel selection policy (``sfw_set_policy``): AUTO switches small grids to the low-latency kernel."""
+        self._check(self._lib.sfw_set_policy(self._ctx, policy))
+
     def set_row_slab(self, row_begin: int, row_end: int):
         self._check(self._lib.sfw_set_row_slab(self._ctx, row_begin, row_end))
 
