@@ -17,13 +17,15 @@ for n_peds in (1, 5, 20, 40):
     if len(sys.argv) > 1:
         wl2 = dataclasses.replace(wl, n_v=int(sys.argv[1]), n_w=int(sys.argv[1]))
         lin, ang = wl2.sample_arrays()
+    from social_force_window_planner_b200._abi import SceneArray
+    sa = SceneArray([sc])  # marshalled once: the timed call is the C ABI call, not Python object building
     s = Scorer(0)
     for _ in range(20):
-        s.score(p, [sc], lin, ang)
+        s.score(p, sa, lin, ang)
     ts = []
     for _ in range(200):
         t0 = time.perf_counter()
-        s.score(p, [sc], lin, ang)
+        s.score(p, sa, lin, ang)
         ts.append(time.perf_counter() - t0)
     s_kernel = s.last_kernel
     s.close()
