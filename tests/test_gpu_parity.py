@@ -396,3 +396,24 @@ def test_kernel_policy(scorer):
         assert np.array_equal(big[0], res["throughput"][0][0]) and np.array_equal(big[399], big[0])
     finally:
         s2.close()
+
+
+@pytest.mark.parametrize("policy", ["throughput", "latency"])
+def test_long_horizon_without_staged_window(scorer, policy):
+    """Reach (max speed x sim_time + footprint radius) beyond what fits the 48 KB shared-memory window: the
+    footprint check reads the costmap from global memory and the free-space shortcut is off."""
+    from social_force_window_planner_b200.scorer import Scorer
+    wl = dataclasses.replace(S.WORKLOADS["C0"], n_v=4, n_w=5, steps=340, n_peds=3, map_w=420, map_h=420)
+    sc = S.make_scene(wl, 2)
+    p = wl.params()
+    lin, ang = wl.sample_arrays(max_vel_x=1.0)
+    p.max_vel_x = 1.0
+    s2 = Scorer(0)
+    try:
+        s2.set_policy(Scorer.POLICY_THROUGHPUT if policy == "throughput" else Scorer.POLICY_LATENCY)
+        costs, best = s2.score(p, [sc], lin, ang)
+        st = parity.compare(p, sc, lin, ang, costs[0], best[0], max_near_frac=1.0)
+        assert 0 < st["valid"] < st["n"] - 1, st  # some rollouts survive 8.5 s, some hit a box
+        print(s2.last_kernel, st)
+    finally:
+        s2.close()
