@@ -200,6 +200,12 @@ int sfw_sync(sfw_ctx *ctx);            /* cudaStreamSynchronize on the context s
 #define SFW_POLICY_LATENCY 2
 int sfw_set_policy(sfw_ctx *ctx, int policy);
 
+/* Rollout prefix sharing (on by default; applies from the next sfw_upload).  With acceleration limits, samples
+ * whose velocity is still ramping at the full +-a*dt per step are identical for their first steps; on dense
+ * multi-wave grids the library simulates those shared prefixes once and starts every sample from the state of
+ * its fork point.  The cost vector is bit-identical either way (same arithmetic, same order). */
+int sfw_set_prefix_sharing(sfw_ctx *ctx, int on);
+
 /* Restrict the next sfw_run calls to linvel rows [row_begin, row_end) of every staged scene
  * (multi-GPU sharding of a single scene across ranks: each rank scores a slab and the winners
  * are all-gathered by the caller).  Rows outside the slab get SFW_COST_SKIPPED. */

@@ -212,6 +212,7 @@ int make_plan(sfw_ctx *c, uint32_t n_scenes, uint32_t samples, uint32_t P, uint3
   pl.win_wp = win_wp;
   pl.win_h = win_h;
   pl.T = T;
+  pl.k = bestK;
   pl.tiles = (samples + T - 1) / T;
   pl.smem = sfw_small_smem_bytes(win_wp, win_h, P, M, F, T);
   pl.valid = true;
@@ -324,6 +325,8 @@ int sfw_destroy(sfw_ctx *c) {
   for (uint32_t q = 0; q < c->xchg.world && c->xchg.connected; ++q)
     if (q != c->xchg.rank && c->xchg.peer[q])
       cudaIpcCloseMemHandle(c->xchg.peer[q]);
+  if (c->share_buf)
+    cudaFree(c->share_buf);
   if (c->xchg.local)
     cudaFree(c->xchg.local);
   if (c->xchg.host)
@@ -429,6 +432,72 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     return fail(c, SFW_ERR_UNSUPPORTED, "num_steps %d > 65535", num_steps);
   const double dt = params->sim_time / num_steps; // :527
 
+  // ---- rollout prefix sharing: leading saturated updates of every row / column (SfwShareDev) ----
+  // Replays the scalar recurrences of step_velocity exactly as the kernel evaluates them (IEEE double add /
+  // compare): update k of row r is "saturated" iff the ramp vi +- a*dt does not reach the target yet.
+  const bool share_candidate = c->share_allowed && c->policy != SFW_POLICY_LATENCY && (uint64_t)n_v * n_w >= 1024 &&
+                               num_steps >= 8;
+  std::vector<uint16_t> sh_kv, sh_kw;
+  std::vector<uint8_t> sh_dv, sh_dw;
+  std::vector<uint32_t> sh_perm, sh_rperm;
+  uint32_t sh_kmax = 0;
+  double sh_mean_s0 = 0.0;
+  if (share_candidate) {
+    const int kcap = std::min(num_steps - 1, 96);
+    auto ramp = [kcap](double target, double v0, double a_dt, uint16_t &k_out, uint8_t &dir_out) {
+      double vi = v0;
+      int k = 0;
+      const bool up = (target - vi) >= 0.0;
+      while (k < kcap && a_dt > 0.0) {
+        const double t = up ? vi + a_dt : vi - a_dt;
+        if (up ? !(target >= t) : !(target <= t))
+          break;
+        vi = t;
+        ++k;
+      }
+      k_out = (uint16_t)k;
+      dir_out = up ? 1 : 0;
+    };
+    const double ax_dt = params->max_trans_acc * dt, ath_dt = params->max_rot_acc * dt;
+    sh_kv.resize((size_t)n_scenes * n_v);
+    sh_dv.resize((size_t)n_scenes * n_v);
+    sh_kw.resize((size_t)n_scenes * n_w);
+    sh_dw.resize((size_t)n_scenes * n_w);
+    for (uint32_t s = 0; s < n_scenes; ++s) {
+      for (uint32_t r = 0; r < n_v; ++r)
+        ramp(linvels[r], scenes[s].robot.vx, ax_dt, sh_kv[(size_t)s * n_v + r], sh_dv[(size_t)s * n_v + r]);
+      for (uint32_t q = 0; q < n_w; ++q)
+        ramp(angvels[q], scenes[s].robot.vtheta, ath_dt, sh_kw[(size_t)s * n_w + q], sh_dw[(size_t)s * n_w + q]);
+    }
+    for (uint16_t k : sh_kv)
+      sh_kmax = std::max<uint32_t>(sh_kmax, k);
+    for (uint16_t k : sh_kw)
+      sh_kmax = std::max<uint32_t>(sh_kmax, k);
+    // lanes of a warp walk columns in the order of their fork step (scene 0's), so that they start together
+    sh_perm.resize(n_w);
+    for (uint32_t q = 0; q < n_w; ++q)
+      sh_perm[q] = q;
+    std::stable_sort(sh_perm.begin(), sh_perm.end(), [&](uint32_t a, uint32_t b) { return sh_kw[a] < sh_kw[b]; });
+    sh_rperm.resize(n_v);
+    for (uint32_t r = 0; r < n_v; ++r)
+      sh_rperm[r] = r;
+    std::stable_sort(sh_rperm.begin(), sh_rperm.end(), [&](uint32_t a, uint32_t b) { return sh_kv[a] < sh_kv[b]; });
+    // what a warp saves: the smallest fork step among its 32 lanes = max(kv[row], min kw of its 32 columns)
+    // (scene 0's tables)
+    double acc = 0.0;
+    uint64_t cnt = 0;
+    for (uint32_t q0 = 0; q0 < n_w; q0 += 32) {
+      uint32_t mkw = 0xffffffffu;
+      for (uint32_t q = q0; q < std::min(q0 + 32, n_w); ++q)
+        mkw = std::min<uint32_t>(mkw, sh_kw[sh_perm[q]]);
+      for (uint32_t r = 0; r < n_v; ++r) {
+        acc += std::max<uint32_t>(sh_kv[r], mkw);
+        ++cnt;
+      }
+    }
+    sh_mean_s0 = cnt ? acc / (double)cnt : 0.0;
+  }
+
   // ---- staged window: everything the footprint can touch ------------------------------------
   double max_lin = 0.0;
   for (uint32_t i = 0; i < n_v; ++i)
@@ -504,6 +573,18 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   off = align_up(off + 8 * (size_t)n_v, kAlign);
   const size_t o_ang = off;
   off = align_up(off + 8 * (size_t)n_w, kAlign);
+  const size_t o_skv = off;
+  off = align_up(off + 2 * sh_kv.size(), kAlign);
+  const size_t o_skw = off;
+  off = align_up(off + 2 * sh_kw.size(), kAlign);
+  const size_t o_sdv = off;
+  off = align_up(off + sh_dv.size(), kAlign);
+  const size_t o_sdw = off;
+  off = align_up(off + sh_dw.size(), kAlign);
+  const size_t o_sperm = off;
+  off = align_up(off + 4 * sh_perm.size(), kAlign);
+  const size_t o_srperm = off;
+  off = align_up(off + 4 * sh_rperm.size(), kAlign);
   const size_t o_maps = off;
   off = align_up(off + slot * n_scenes, kAlign);
   const size_t in_bytes = off;
@@ -524,6 +605,14 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   double2 *hF = reinterpret_cast<double2 *>(h + o_fp);
   if (!grp_table.empty())
     memcpy(h + o_grp, grp_table.data(), 4 * grp_table.size());
+  if (share_candidate) {
+    memcpy(h + o_skv, sh_kv.data(), 2 * sh_kv.size());
+    memcpy(h + o_skw, sh_kw.data(), 2 * sh_kw.size());
+    memcpy(h + o_sdv, sh_dv.data(), sh_dv.size());
+    memcpy(h + o_sdw, sh_dw.data(), sh_dw.size());
+    memcpy(h + o_sperm, sh_perm.data(), 4 * sh_perm.size());
+    memcpy(h + o_srperm, sh_rperm.data(), 4 * sh_rperm.size());
+  }
   memcpy(h + o_lin, linvels, 8 * (size_t)n_v);
   memcpy(h + o_ang, angvels, 8 * (size_t)n_w);
   uint32_t pP = 0, pM = 0, pF = 0;
@@ -717,6 +806,47 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   B.k_gaze = (float)sfm.force_factor_group_gaze;
   B.k_coh = (float)sfm.force_factor_group_coherence;
   B.k_rep = (float)sfm.force_factor_group_repulsion;
+  // ---- prefix sharing: worth it?  It removes mean_s0 of num_steps steps from every warp, and costs two
+  // latency-bound launches of kmax steps each; a launch that fits one wave ends with its slowest block anyway.
+  c->share_active = false;
+  if (share_candidate && !c->plan.crowd && sh_kmax >= 2) {
+    const double P = (double)maxP;
+    const double total = (double)n_scenes * samples;
+    const double resident = (double)c->sm_count * c->plan.k * c->plan.T;
+    const double t_ts_ns = 0.1 + 0.017 * P + 0.0008 * P * P;              // throughput cost of one trajectory-step
+    const double t_lat_us = 1.3 + 0.25 * P + 0.028 * P * P;               // one step of a lone warp
+    const double saved_us = total * sh_mean_s0 * t_ts_ns * 1e-3;
+    const double cost_us = 2.0 * sh_kmax * t_lat_us + 30.0;
+    const uint32_t paths = 4u + 2u * n_w + 2u * n_v;
+    const uint32_t P2max = (maxP + 1u) / 2u;
+    const uint32_t rec = (uint32_t)align_up(sizeof(SfwCkptHdr) + 32u * P2max, 16);
+    const size_t need = (size_t)n_scenes * paths * (sh_kmax + 1u) * rec;
+    if (total >= 2.5 * resident && saved_us > 2.0 * cost_us && need <= ((size_t)8 << 30)) {
+      if (need > c->share_cap) {
+        CK(c, cudaStreamSynchronize(c->stream));
+        if (c->share_buf)
+          cudaFree(c->share_buf);
+        c->share_buf = nullptr;
+        c->share_cap = 0;
+        CK(c, cudaMalloc((void **)&c->share_buf, need));
+        c->share_cap = need;
+      }
+      B.share.records = c->share_buf;
+      B.share.kv = reinterpret_cast<const uint16_t *>(dv + o_skv);
+      B.share.kw = reinterpret_cast<const uint16_t *>(dv + o_skw);
+      B.share.dirv = dv + o_sdv;
+      B.share.dirw = dv + o_sdw;
+      B.share.col_perm = reinterpret_cast<const uint32_t *>(dv + o_sperm);
+      B.share.row_perm = reinterpret_cast<const uint32_t *>(dv + o_srperm);
+      B.share.scene_stride = (uint64_t)paths * (sh_kmax + 1u) * rec;
+      B.share.rec_bytes = rec;
+      B.share.kmax = sh_kmax;
+      B.share.mode = 0;
+      c->share_active = true;
+      c->share_paths = paths;
+      c->share_mean_s0 = sh_mean_s0;
+    }
+  }
   if (win_wp) {
     rc = make_tensor_map(c, B.maps, map_pitch, map_rows, n_scenes, win_wp, win_h);
     if (rc != SFW_OK)
@@ -745,6 +875,14 @@ int sfw_set_policy(sfw_ctx *c, int policy) {
     return fail(c, SFW_ERR_ARG, "sfw_set_policy: unknown policy %d", policy);
   c->policy = policy;
   c->plan.valid = false;
+  return SFW_OK;
+}
+
+int sfw_set_prefix_sharing(sfw_ctx *c, int on) {
+  if (!c)
+    return SFW_ERR_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->share_allowed = on != 0;
   return SFW_OK;
 }
 
@@ -824,8 +962,31 @@ int sfw_run(sfw_ctx *c) {
                            c->plan.smem, c->stream));
     c->launches += 2; // scorer + arg-min
     c->last_kernel = "sfw_score_crowd";
+  } else if (re > rb && c->share_active && rb == 0 && re == B.n_v) {
+    // rollout prefix sharing: the 4 doubly saturated paths, the 2 (n_v + n_w) singly saturated ones (each
+    // continuing one of the 4), then every sample from the record of its own fork point
+    // (the path launches are latency bound: small blocks, so that every scene's few paths are resident at once)
+    SfwBatchDev W = B;
+    const uint32_t T1 = 32, T2 = 128;
+    W.share.mode = 1;
+    W.tiles_per_scene = 1;
+    CK(c, sfw_launch_small(W, c->tmap, T1,
+                           sfw_small_smem_bytes(B.win_wp, B.win_h, c->plan.maxP, c->plan.maxM, c->plan.maxF, T1),
+                           c->stream));
+    W.share.mode = 2;
+    W.tiles_per_scene = (c->share_paths - 4u + T2 - 1u) / T2;
+    CK(c, sfw_launch_small(W, c->tmap, T2,
+                           sfw_small_smem_bytes(B.win_wp, B.win_h, c->plan.maxP, c->plan.maxM, c->plan.maxF, T2),
+                           c->stream));
+    W.share.mode = 3;
+    W.tiles_per_scene = B.tiles_per_scene;
+    CK(c, sfw_launch_small(W, c->tmap, c->plan.T, c->plan.smem, c->stream));
+    c->launches += 3;
+    c->last_kernel = sfw_small_kernel_name(c->plan.T, true);
   } else if (re > rb) {
-    CK(c, sfw_launch_small(B, c->tmap, c->plan.T, c->plan.smem, c->stream));
+    SfwBatchDev W = B;
+    W.share.mode = 0;
+    CK(c, sfw_launch_small(W, c->tmap, c->plan.T, c->plan.smem, c->stream));
     c->launches += 1;
     c->last_kernel = sfw_small_kernel_name(c->plan.T);
   } else {

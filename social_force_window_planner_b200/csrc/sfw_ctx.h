@@ -23,7 +23,7 @@ struct SfwPlan {
   // shape key
   uint32_t n_scenes = 0, samples = 0, maxP = 0, maxM = 0, maxF = 0, win_wp = 0, win_h = 0;
   // result
-  uint32_t T = 0, tiles = 0;
+  uint32_t T = 0, tiles = 0, k = 1;
   size_t smem = 0;
   bool crowd = false; // block-per-trajectory kernel (sfw_crowd.cu)
   uint32_t grid = 0;
@@ -44,6 +44,14 @@ struct sfw_ctx {
   SfwArena sensor_in, sensor_out; // sfw_laser_obstacles / sfw_marker_points staging
   bool laser_attr_set = false;
   int policy = 0; // SFW_POLICY_*
+
+  // rollout prefix sharing (SfwShareDev)
+  bool share_allowed = true; // sfw_set_prefix_sharing
+  bool share_active = false; // decided per upload
+  uint8_t *share_buf = nullptr;
+  size_t share_cap = 0;
+  uint32_t share_paths = 0;
+  double share_mean_s0 = 0.0;
 
   // fused multi-GPU winner exchange (csrc/sfw_exchange.cu)
   struct {

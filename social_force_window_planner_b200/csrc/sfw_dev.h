@@ -64,6 +64,35 @@ struct SfwExchangeDev {
   uint32_t slot, pad0;                       // epoch parity of this launch
 };
 
+// Rollout prefix sharing (thread-per-trajectory kernel, DESIGN.md 4.1 "prefix sharing").  The accel-limited
+// unicycle makes many samples identical for their first steps: while a sample's linear (angular) velocity is
+// still ramping at the full +-a*dt per step it is indistinguishable from every other sample that ramps the same
+// way.  kv[r] / kw[c] = number of leading fully saturated updates of row r / column c, dirv / dirw = their
+// direction.  Sample (r, c) is bit-identical to a SHARED path for its first max(kv, kw) steps:
+//   steps <= min(kv, kw): one of the 4 doubly saturated paths              (records region A)
+//   then, until max:      the path "v saturated, w as column c" (region B) or "v as row r, w saturated" (C)
+// Launch 1 simulates A, launch 2 B and C (each starting from an A record), launch 3 the samples themselves,
+// each from the record of its own fork point.  A record = SfwCkptHdr + (pos, vel) float4 per pedestrian pair.
+struct SfwCkptHdr {
+  double x, y, th, vx, vth, social_work, costmap_sum;
+  float prx, pry, rvxf, rvyf;
+  uint64_t goalmask;
+  int32_t npts, alive;
+  uint64_t pad;
+};
+struct SfwShareDev {
+  uint8_t *records;         // [scene][4 + 2 n_w + 2 n_v paths][kmax + 1 step counts][rec_bytes]
+  const uint16_t *kv, *kw;  // [scene][n_v], [scene][n_w]
+  const uint8_t *dirv, *dirw; // 1 = ramping up
+  // launch 3 walks the grid in fork-step order: a warp = 32 consecutive columns of col_perm (sorted by kw) on one
+  // row, consecutive warps = consecutive rows of row_perm (sorted by kv) on the same 32 columns -> the lanes of a
+  // warp and the warps of a block start (and finish) together
+  const uint32_t *col_perm, *row_perm;
+  uint64_t scene_stride;
+  uint32_t rec_bytes, kmax;
+  uint32_t mode, pad0;      // 0 off, 1 / 2 path writers, 3 reader
+};
+
 struct SfwBatchDev {
   const SfwSceneDev *scenes;
   // pedestrians are stored as PAIRS (2k, 2k+1), one float4 per pair and quantity, so that the two
@@ -111,6 +140,7 @@ struct SfwBatchDev {
   float k_gaze, k_coh, k_rep; // forceFactorGroupGaze / Coherence / Repulsion
   float pad2;
   SfwExchangeDev xchg;
+  SfwShareDev share;
 };
 
 #endif

@@ -47,7 +47,11 @@
 // MAXT: largest block the variant may be launched with.  One block per SM is resident (the per-thread
 // shared-memory columns fill the SM), so the register budget is 64K / MAXT: 512 -> 128, 448 -> 144,
 // 384 -> 168.  The host picks the variant with the most registers that still covers its block size.
-template <int MAXT>
+// SHARE: rollout prefix sharing (SfwShareDev): the same kernel simulates the shared paths and writes their
+// per-step records (B.share.mode 1, 2) or starts every sample from the record of its fork point (mode 3).
+// The plain instantiation compiles all of that out.
+#define SFW_HUGE_TARGET 1.0e300 /* velocity target that keeps step_velocity saturated for ever */
+template <int MAXT, bool SHARE>
 __global__ void __launch_bounds__(MAXT, 1)
 sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -181,14 +185,82 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   // ---- which trajectory is mine ----------------------------------------------------------------
   const uint32_t n_w = B.n_w;
   const uint32_t first = B.row_begin * n_w, last = B.row_end * n_w;
-  const uint32_t idx = first + tile * T + tid;
-  const bool in_range = idx < last;
+  uint32_t idx = first + tile * T + tid;
+  bool in_range = idx < last;
   double v_s = 0.0, w_s = 0.0;
-  if (in_range) {
+  int s0 = 0;                           // first step this thread simulates itself
+  const uint8_t *ck_in = nullptr;       // record it starts from (nullptr: the scene's initial state)
+  uint8_t *ck_out = nullptr;            // writer launches: this path's records [step count]
+  const uint32_t share_mode = SHARE ? B.share.mode : 0u;
+  const bool writer = SHARE && (share_mode == 1u || share_mode == 2u);
+  if (SHARE && share_mode) {
+    const SfwShareDev &H = B.share;
+    const uint16_t *kv = H.kv + (size_t)scene * B.n_v, *kw = H.kw + (size_t)scene * n_w;
+    const uint8_t *dirv = H.dirv + (size_t)scene * B.n_v, *dirw = H.dirw + (size_t)scene * n_w;
+    uint8_t *base = H.records + (size_t)scene * H.scene_stride;
+    const size_t R = H.rec_bytes, K1 = (size_t)H.kmax + 1u;
+    const uint32_t p = tile * T + tid; // writer launches: path number
+    if (share_mode == 3u) {
+      if (in_range) {
+        uint32_t r, c;
+        if ((n_w & 31u) == 0u) { // warp-major walk: 32 sorted columns x sorted rows
+          const uint32_t w = idx >> 5, chunk = w / B.n_v;
+          r = H.row_perm[w - chunk * B.n_v];
+          c = H.col_perm[chunk * 32u + (idx & 31u)];
+        } else {
+          r = idx / n_w;
+          c = H.col_perm[idx - r * n_w];
+        }
+        idx = r * n_w + c;
+        v_s = B.linvels[r];
+        w_s = B.angvels[c];
+        const int kvr = kv[r], kwc = kw[c];
+        s0 = max(kvr, kwc);
+        if (s0 > 0) {
+          size_t path;
+          if (kvr == kwc)
+            path = (size_t)dirv[r] * 2u + dirw[c];
+          else if (kvr > kwc)
+            path = 4u + (size_t)dirv[r] * n_w + c;
+          else
+            path = 4u + 2u * (size_t)n_w + (size_t)r * 2u + dirw[c];
+          ck_in = base + (path * K1 + (size_t)s0) * R;
+        }
+      }
+    } else if (share_mode == 1u) { // the 4 doubly saturated paths
+      in_range = p < 4u;
+      if (in_range) {
+        v_s = (p >> 1) ? SFW_HUGE_TARGET : -SFW_HUGE_TARGET;
+        w_s = (p & 1u) ? SFW_HUGE_TARGET : -SFW_HUGE_TARGET;
+        ck_out = base + (size_t)p * K1 * R;
+      }
+    } else { // mode 2: (v saturated, column c) and (row r, w saturated)
+      in_range = p < 2u * n_w + 2u * B.n_v;
+      if (in_range) {
+        size_t parent;
+        if (p < 2u * n_w) {
+          const uint32_t dv = p / n_w, c = p - dv * n_w;
+          v_s = dv ? SFW_HUGE_TARGET : -SFW_HUGE_TARGET;
+          w_s = B.angvels[c];
+          s0 = kw[c];
+          parent = (size_t)dv * 2u + dirw[c];
+        } else {
+          const uint32_t q = p - 2u * n_w, r = q >> 1, dw = q & 1u;
+          v_s = B.linvels[r];
+          w_s = dw ? SFW_HUGE_TARGET : -SFW_HUGE_TARGET;
+          s0 = kv[r];
+          parent = (size_t)dirv[r] * 2u + dw;
+        }
+        if (s0 > 0)
+          ck_in = base + (parent * K1 + (size_t)s0) * R;
+        ck_out = base + (4u + (size_t)p) * K1 * R;
+      }
+    }
+  } else if (in_range) {
     v_s = B.linvels[idx / n_w];
     w_s = B.angvels[idx % n_w];
   }
-  const bool skipped = in_range && (v_s == 0.0 && w_s == 0.0); // sfw_planner.cpp:349-352
+  const bool skipped = !writer && in_range && (v_s == 0.0 && w_s == 0.0); // sfw_planner.cpp:349-352
   bool alive = in_range && !skipped;
 
   // ---- per-thread state: one shared-memory column per thread (conflict-free LDS.128) ------------
@@ -214,10 +286,37 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   double social_work = 0.0, costmap_sum = 0.0;
   int npts = 0;
   const int S = B.num_steps;
+  if (SHARE && ck_in) { // start from the shared path's record of this thread's fork point
+    const SfwCkptHdr *h = reinterpret_cast<const SfwCkptHdr *>(ck_in);
+    x = h->x;
+    y = h->y;
+    th = h->th;
+    vx = h->vx;
+    vth = h->vth;
+    social_work = h->social_work;
+    costmap_sum = h->costmap_sum;
+    prx = h->prx;
+    pry = h->pry;
+    rvxf = h->rvxf;
+    rvyf = h->rvyf;
+    goalmask = h->goalmask;
+    npts = h->npts;
+    alive = alive && h->alive != 0;
+    const float4 *pv = reinterpret_cast<const float4 *>(ck_in + sizeof(SfwCkptHdr));
+    for (uint32_t k = 0; k < P2; ++k) {
+      pos[k * T] = pv[2u * k];
+      vel[k * T] = pv[2u * k + 1u];
+    }
+  }
+  const int S_end = writer ? (int)B.share.kmax : S;
+  const int i_first = SHARE ? __reduce_min_sync(0xffffffffu, in_range ? s0 : S_end) : 0;
 
-  for (int i = 0; i < S; ++i) {
-    if (!__any_sync(0xffffffffu, alive))
+  for (int i = i_first; i < S_end; ++i) {
+    if (!writer && !__any_sync(0xffffffffu, alive))
       break;
+    const bool started = !SHARE || i >= s0; // lanes of a warp may fork at different steps
+    const bool was_alive = alive;
+    alive = alive && started;
     // -- legality of the current pose (sfw_planner.cpp:545-575) --
     double sn = 0.0, cs = 1.0;
     int fc = -1;
@@ -403,7 +502,38 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
           alive = false;
       }
     }
+    if (SHARE) {
+      if (!started)
+        alive = was_alive; // not forked yet: untouched
+      if (writer && in_range && started) { // the path's state after i + 1 steps
+        uint8_t *rec = ck_out + (size_t)(i + 1) * B.share.rec_bytes;
+        SfwCkptHdr *h = reinterpret_cast<SfwCkptHdr *>(rec);
+        h->x = x;
+        h->y = y;
+        h->th = th;
+        h->vx = vx;
+        h->vth = vth;
+        h->social_work = social_work;
+        h->costmap_sum = costmap_sum;
+        h->prx = prx;
+        h->pry = pry;
+        h->rvxf = rvxf;
+        h->rvyf = rvyf;
+        h->goalmask = goalmask;
+        h->npts = npts;
+        h->alive = alive ? 1 : 0;
+        if (alive) {
+          float4 *pv = reinterpret_cast<float4 *>(rec + sizeof(SfwCkptHdr));
+          for (uint32_t k = 0; k < P2; ++k) {
+            pv[2u * k] = pos[k * T];
+            pv[2u * k + 1u] = vel[k * T];
+          }
+        }
+      }
+    }
   }
+  if (writer)
+    return; // shared paths have no cost of their own
 
   // ---- terminal costs (sfw_planner.cpp:643-675) -----------------------------------------------
   float cost = in_range ? (skipped ? SFW_COST_SKIPPED : SFW_COST_INVALID) : SFW_COST_SKIPPED;
@@ -620,19 +750,25 @@ struct SmallVariant {
   const char *name;
 };
 const SmallVariant kSmall[] = {
-    {384, sfw_score_small<384>, "sfw_score_small<384>"},
-    {448, sfw_score_small<448>, "sfw_score_small<448>"},
-    {512, sfw_score_small<512>, "sfw_score_small<512>"},
+    {384, sfw_score_small<384, false>, "sfw_score_small<384>"},
+    {448, sfw_score_small<448, false>, "sfw_score_small<448>"},
+    {512, sfw_score_small<512, false>, "sfw_score_small<512>"},
 };
-const SmallVariant &small_variant(uint32_t T) {
-  for (const SmallVariant &v : kSmall)
-    if (T <= v.maxt)
-      return v;
-  return kSmall[2];
+const SmallVariant kSmallShare[] = {
+    {384, sfw_score_small<384, true>, "sfw_score_small<384,share>"},
+    {448, sfw_score_small<448, true>, "sfw_score_small<448,share>"},
+    {512, sfw_score_small<512, true>, "sfw_score_small<512,share>"},
+};
+const SmallVariant &small_variant(uint32_t T, bool share = false) {
+  const SmallVariant *tab = share ? kSmallShare : kSmall;
+  for (int i = 0; i < 3; ++i)
+    if (T <= tab[i].maxt)
+      return tab[i];
+  return tab[2];
 }
 } // namespace
 
-const char *sfw_small_kernel_name(uint32_t T) { return small_variant(T).name; }
+const char *sfw_small_kernel_name(uint32_t T, bool share) { return small_variant(T, share).name; }
 
 // Largest dynamic shared memory a block of sfw_score_small may request on the current device
 // (opt-in limit minus the kernel's static shared memory); also opts every variant in.
@@ -647,18 +783,20 @@ cudaError_t sfw_small_max_dynamic_smem(size_t *bytes) {
     if (e != cudaSuccess)
       return e;
     size_t dyn = (size_t)optin;
-    for (const SmallVariant &v : kSmall) {
-      cudaFuncAttributes fa;
-      e = cudaFuncGetAttributes(&fa, v.fn);
-      if (e != cudaSuccess)
-        return e;
-      dyn = std::min(dyn, (size_t)optin - fa.sharedSizeBytes);
-    }
-    for (const SmallVariant &v : kSmall) {
-      e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-      if (e != cudaSuccess)
-        return e;
-    }
+    for (const SmallVariant *tab : {kSmall, kSmallShare})
+      for (int i = 0; i < 3; ++i) {
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, tab[i].fn);
+        if (e != cudaSuccess)
+          return e;
+        dyn = std::min(dyn, (size_t)optin - fa.sharedSizeBytes);
+      }
+    for (const SmallVariant *tab : {kSmall, kSmallShare})
+      for (int i = 0; i < 3; ++i) {
+        e = cudaFuncSetAttribute(tab[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess)
+          return e;
+      }
     cached = dyn;
   }
   *bytes = cached;
@@ -668,13 +806,18 @@ cudaError_t sfw_small_max_dynamic_smem(size_t *bytes) {
 cudaError_t sfw_launch_small(const SfwBatchDev &B, const CUtensorMap &tmap, uint32_t T,
                              size_t smem_bytes, cudaStream_t stream) {
   const uint32_t grid = B.n_scenes * B.tiles_per_scene;
-  small_variant(T).fn<<<grid, T, smem_bytes, stream>>>(B, tmap);
+  small_variant(T, B.share.mode != 0).fn<<<grid, T, smem_bytes, stream>>>(B, tmap);
   return cudaGetLastError();
 }
 
 cudaError_t sfw_small_occupancy(uint32_t T, size_t smem_bytes, int *blocks_per_sm) {
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, small_variant(T).fn, (int)T,
-                                                       smem_bytes);
+  int a = 0, b = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, small_variant(T, false).fn, (int)T, smem_bytes);
+  if (e != cudaSuccess)
+    return e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, small_variant(T, true).fn, (int)T, smem_bytes);
+  *blocks_per_sm = std::min(a, b);
+  return e;
 }
 
 cudaError_t sfw_launch_points(const SfwBatchDev &B, uint32_t scene, uint32_t idx, uint32_t n_points,

@@ -70,6 +70,10 @@ class Scorer:
         """Kernel selection policy (``sfw_set_policy``): AUTO switches small grids to the low-latency kernel."""
         self._check(self._lib.sfw_set_policy(self._ctx, policy))
 
+    def set_prefix_sharing(self, on: bool):
+        """Rollout prefix sharing on dense multi-wave grids (``sfw_set_prefix_sharing``); bit-identical results."""
+        self._check(self._lib.sfw_set_prefix_sharing(self._ctx, 1 if on else 0))
+
     def set_row_slab(self, row_begin: int, row_end: int):
         self._check(self._lib.sfw_set_row_slab(self._ctx, row_begin, row_end))
 

@@ -417,3 +417,39 @@ def test_long_horizon_without_staged_window(scorer, policy):
         print(s2.last_kernel, st)
     finally:
         s2.close()
+
+
+# ---- rollout prefix sharing -------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,n_scenes", [("C4", 1), ("C3", 64)])
+def test_prefix_sharing_is_bit_identical(name, n_scenes):
+    """Dense multi-wave grids start every sample from the shared state of its fork point (SfwShareDev): same
+    arithmetic in the same order, so the cost vector, the recorded-point counts and the winners must equal the
+    unshared run bit for bit — and the shared run must actually have been taken."""
+    from social_force_window_planner_b200.scorer import Scorer
+    wl = S.WORKLOADS[name]
+    scs = S.make_scenes(wl, n_scenes)
+    if n_scenes > 1:  # different odometry per scene: per-scene fork tables
+        for k, sc in enumerate(scs):
+            r = list(sc.robot)
+            r[3] = float(np.float32(0.05 + 0.6 * (k % 7) / 6.0))
+            r[5] = float(np.float32(-0.4 + 0.8 * (k % 5) / 4.0))
+            r[10] = r[3]
+            sc.robot = tuple(r)
+    p = wl.params()
+    lin, ang = wl.sample_arrays()
+    s2 = Scorer(0)
+    try:
+        costs_on, best_on = s2.score(p, scs, lin, ang)
+        k_on = s2.last_kernel
+        pts_on = [s2.trajectory_points(0, i)[1] for i in (0, 777, wl.samples - 1)]
+        s2.set_prefix_sharing(False)
+        costs_off, best_off = s2.score(p, scs, lin, ang)
+        k_off = s2.last_kernel
+        pts_off = [s2.trajectory_points(0, i)[1] for i in (0, 777, wl.samples - 1)]
+    finally:
+        s2.close()
+    assert "share" in k_on and "share" not in k_off, (k_on, k_off)
+    assert np.array_equal(costs_on, costs_off)
+    assert np.array_equal(best_on, best_off)
+    assert pts_on == pts_off
+    print(name, k_on, "valid", float((costs_on >= 0).mean()))
