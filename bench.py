@@ -347,12 +347,15 @@ def main():
         algo_bytes = scorer.algorithmic_bytes
 
         # ---- end-to-end arm: host buffers in, host cost vector + winner out, every step ----------------
+        from social_force_window_planner_b200._abi import SceneArray
+        scene_host = SceneArray([scene])  # the caller's SfwScene structs over its host buffers (built once, like a
+        #                                   C++ caller's); every call below still packs + copies them to the device
         for _ in range(3):
-            scorer.score(params, [scene], lin, ang, want_costs=True)
+            scorer.score(params, scene_host, lin, ang, want_costs=True)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            costs_e2e, best_e2e = scorer.score(params, [scene], lin, ang, want_costs=True)
+            costs_e2e, best_e2e = scorer.score(params, scene_host, lin, ang, want_costs=True)
             if world > 1:
                 gather_winners()
                 torch.cuda.current_stream().synchronize()
