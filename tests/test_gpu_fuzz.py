@@ -54,3 +54,27 @@ def test_random_scene_vs_oracle(scorer, seed):
     costs, best = scorer.score(p, [sc], lin, ang)
     st = parity.compare(p, sc, lin, ang, costs[0], best[0], max_near_frac=1.0)
     print(seed, wl.n_peds, "peds", len(sc.obstacles), "obst", wl.steps, "steps", scorer.last_kernel, st)
+
+
+@pytest.mark.parametrize("seed", range(0, 28, 2))
+def test_random_scene_latency_policy(seed):
+    """The same random shapes through the block-per-trajectory kernel (SFW_POLICY_LATENCY), which AUTO only picks
+    for small grids and big crowds: empty crowds, single pedestrians, point footprints, no obstacles ..."""
+    from social_force_window_planner_b200.scorer import Scorer
+    wl, p, sc, lin, ang = _random_case(seed)
+    s2 = Scorer(0)
+    try:
+        s2.set_policy(Scorer.POLICY_LATENCY)
+        costs, best = s2.score(p, [sc], lin, ang)
+        assert s2.last_kernel == "sfw_score_crowd"
+        st = parity.compare(p, sc, lin, ang, costs[0], best[0], max_near_frac=1.0)
+        # and the thread-per-trajectory kernel on the same scene agrees with it (same model, other summation order)
+        if wl.n_peds <= 64:
+            s2.set_policy(Scorer.POLICY_THROUGHPUT)
+            c2, b2 = s2.score(p, [sc], lin, ang)
+            clear = (costs[0] >= 0) & (c2[0] >= 0)
+            if clear.any():
+                assert np.max(np.abs(costs[0][clear] - c2[0][clear]) / np.abs(c2[0][clear])) < 5e-2
+    finally:
+        s2.close()
+    print(seed, wl.n_peds, "peds", st)
