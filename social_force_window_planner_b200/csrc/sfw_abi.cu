@@ -809,17 +809,22 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   // ---- prefix sharing: worth it?  It removes mean_s0 of num_steps steps from every warp, and costs two
   // latency-bound launches of kmax steps each; a launch that fits one wave ends with its slowest block anyway.
   c->share_active = false;
-  if (share_candidate && !c->plan.crowd && sh_kmax >= 2) {
+  if (share_candidate && sh_kmax >= 2) {
+    const bool crowd = c->plan.crowd;
     const double P = (double)maxP;
     const double total = (double)n_scenes * samples;
-    const double resident = (double)c->sm_count * c->plan.k * c->plan.T;
-    const double t_ts_ns = 0.1 + 0.017 * P + 0.0008 * P * P;              // throughput cost of one trajectory-step
-    const double t_lat_us = 1.3 + 0.25 * P + 0.028 * P * P;               // one step of a lone warp
-    const double saved_us = total * sh_mean_s0 * t_ts_ns * 1e-3;
-    const double cost_us = 2.0 * sh_kmax * t_lat_us + 30.0;
     const uint32_t paths = 4u + 2u * n_w + 2u * n_v;
     const uint32_t P2max = (maxP + 1u) / 2u;
-    const uint32_t rec = (uint32_t)align_up(sizeof(SfwCkptHdr) + 32u * P2max, 16);
+    // thread-per-trajectory: throughput cost of a trajectory-step / one step of a lone warp;
+    // block-per-trajectory: a trajectory-step at full occupancy / one step of one block
+    const double resident = crowd ? (double)c->plan.grid : (double)c->sm_count * c->plan.k * c->plan.T;
+    const double t_ts_ns = crowd ? 0.2 + 0.00085 * P * P : 0.1 + 0.017 * P + 0.0008 * P * P;
+    const double t_lat_us = crowd ? 2.0 + 0.00025 * P * P : 1.3 + 0.25 * P + 0.028 * P * P;
+    const double path_waves = crowd ? std::ceil((double)n_scenes * paths / resident) : 1.0;
+    const double saved_us = total * sh_mean_s0 * t_ts_ns * 1e-3;
+    const double cost_us = (1.0 + path_waves) * sh_kmax * t_lat_us + 30.0;
+    const uint32_t rec = crowd ? (uint32_t)align_up(16u + 32u * P2max + 2u * P2max, 16)
+                               : (uint32_t)align_up(sizeof(SfwCkptHdr) + 32u * P2max, 16);
     const size_t need = (size_t)n_scenes * paths * (sh_kmax + 1u) * rec;
     if (total >= 2.5 * resident && saved_us > 2.0 * cost_us && need <= ((size_t)8 << 30)) {
       if (need > c->share_cap) {
@@ -957,9 +962,22 @@ int sfw_run(sfw_ctx *c) {
     c->xchg.epoch += 1;
     c->xchg.expected += B.n_scenes; // every rank stages the same number of scenes per tick
   }
-  if (re > rb && c->plan.crowd) {
-    CK(c, sfw_launch_crowd(B, reinterpret_cast<unsigned int *>(c->out.dev + c->off_work), c->plan.grid,
-                           c->plan.smem, c->stream));
+  if (re > rb && c->plan.crowd && c->share_active && rb == 0 && re == B.n_v) {
+    // rollout prefix sharing, block-per-trajectory flavour: paths, paths, samples (+ arg-min)
+    unsigned int *wc = reinterpret_cast<unsigned int *>(c->out.dev + c->off_work);
+    SfwBatchDev W = B;
+    for (uint32_t mode = 1; mode <= 3; ++mode) {
+      W.share.mode = mode;
+      const uint64_t items = (uint64_t)B.n_scenes * (mode == 1 ? 4u : mode == 2 ? c->share_paths - 4u : c->out_samples);
+      CK(c, sfw_launch_crowd(W, wc, (uint32_t)std::min<uint64_t>(items, c->plan.grid), c->plan.smem, c->stream, mode == 3));
+    }
+    c->launches += 4;
+    c->last_kernel = "sfw_score_crowd,share";
+  } else if (re > rb && c->plan.crowd) {
+    SfwBatchDev W = B;
+    W.share.mode = 0;
+    CK(c, sfw_launch_crowd(W, reinterpret_cast<unsigned int *>(c->out.dev + c->off_work), c->plan.grid,
+                           c->plan.smem, c->stream, true));
     c->launches += 2; // scorer + arg-min
     c->last_kernel = "sfw_score_crowd";
   } else if (re > rb && c->share_active && rb == 0 && re == B.n_v) {

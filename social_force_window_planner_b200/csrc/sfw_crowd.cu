@@ -93,7 +93,15 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t n_w = B.n_w;
-  const uint32_t per_scene = (B.row_end - B.row_begin) * n_w;
+  // Rollout prefix sharing (SfwShareDev): mode 1 / 2 items are shared paths that write a record per step,
+  // mode 3 items are the samples, each starting from the record of its fork point.  A record here is
+  // {double social_work; int alive; int steps_done} + pos[P2] + vel[P2] (float4) + goal flags (2 P2 bytes):
+  // the robot rollout and the footprint checks are recomputed per item in the prologue anyway.
+  const uint32_t share_mode = B.share.mode;
+  const bool writer = share_mode == 1u || share_mode == 2u;
+  const uint32_t per_scene = share_mode == 1u   ? 4u
+                             : share_mode == 2u ? 2u * n_w + 2u * B.n_v
+                                                : (B.row_end - B.row_begin) * n_w;
   const uint32_t total = B.n_scenes * per_scene;
   const int S = B.num_steps;
   const SfmConst K = make_sfm_const(B);
@@ -112,14 +120,60 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
     if (item >= total)
       break;
     const uint32_t scene = item / per_scene;
-    const uint32_t idx = B.row_begin * n_w + (item - scene * per_scene);
+    const uint32_t local = item - scene * per_scene;
+    const uint32_t idx = B.row_begin * n_w + local;
     const SfwSceneDev *__restrict__ scp = B.scenes + scene;
     const uint32_t P2 = scp->n_pairs, M = scp->n_obst, F = scp->n_fp;
     const uint32_t n_groups = scp->n_groups;
     const CrowdSmem sm = carve(smem_raw, P2, M, F, (uint32_t)S);
-    const double v_s = B.linvels[idx / n_w], w_s = B.angvels[idx % n_w];
+    double v_s, w_s;
+    int s0 = 0;                     // first step this item simulates itself
+    const uint8_t *rec_in = nullptr; // record it starts from
+    uint8_t *rec_out = nullptr;     // writer items: this path's records [step count]
+    if (share_mode) {
+      const SfwShareDev &H = B.share;
+      const uint16_t *kv = H.kv + (size_t)scene * B.n_v, *kw = H.kw + (size_t)scene * n_w;
+      const uint8_t *dirv = H.dirv + (size_t)scene * B.n_v, *dirw = H.dirw + (size_t)scene * n_w;
+      uint8_t *base = H.records + (size_t)scene * H.scene_stride;
+      const size_t R = H.rec_bytes, K1 = (size_t)H.kmax + 1u;
+      size_t parent = 0;
+      if (share_mode == 3u) {
+        const uint32_t r = idx / n_w, c = idx - r * n_w;
+        v_s = B.linvels[r];
+        w_s = B.angvels[c];
+        const int kvr = kv[r], kwc = kw[c];
+        s0 = max(kvr, kwc);
+        parent = kvr == kwc  ? (size_t)dirv[r] * 2u + dirw[c]
+                 : kvr > kwc ? 4u + (size_t)dirv[r] * n_w + c
+                             : 4u + 2u * (size_t)n_w + (size_t)r * 2u + dirw[c];
+      } else if (share_mode == 1u) {
+        v_s = (local >> 1) ? 1.0e300 : -1.0e300;
+        w_s = (local & 1u) ? 1.0e300 : -1.0e300;
+        rec_out = base + (size_t)local * K1 * R;
+      } else if (local < 2u * n_w) {
+        const uint32_t dv = local / n_w, c = local - dv * n_w;
+        v_s = dv ? 1.0e300 : -1.0e300;
+        w_s = B.angvels[c];
+        s0 = kw[c];
+        parent = (size_t)dv * 2u + dirw[c];
+        rec_out = base + (4u + (size_t)local) * K1 * R;
+      } else {
+        const uint32_t q = local - 2u * n_w, r = q >> 1, dw = q & 1u;
+        v_s = B.linvels[r];
+        w_s = dw ? 1.0e300 : -1.0e300;
+        s0 = kv[r];
+        parent = (size_t)dirv[r] * 2u + dw;
+        rec_out = base + (4u + (size_t)local) * K1 * R;
+      }
+      if (s0 > 0)
+        rec_in = base + (parent * K1 + (size_t)s0) * R;
+    } else {
+      v_s = B.linvels[idx / n_w];
+      w_s = B.angvels[idx % n_w];
+    }
+    const int n_run = writer ? (int)B.share.kmax : S; // steps this item is asked to reach
     const size_t out = (size_t)scene * B.n_v * n_w + idx;
-    if (v_s == 0.0 && w_s == 0.0) { // sfw_planner.cpp:349-352
+    if (!writer && v_s == 0.0 && w_s == 0.0) { // sfw_planner.cpp:349-352
       if (tid == 0) {
         B.costs[out] = SFW_COST_SKIPPED;
         B.npts[out] = 0;
@@ -128,11 +182,13 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
     }
 
     // ---- stage the scene (static part once per scene, state every item) ----------------------
+    const float4 *rec_pv = rec_in ? reinterpret_cast<const float4 *>(rec_in + 16) : nullptr;
+    const uint8_t *rec_gf = rec_in ? rec_in + 16 + 32u * (size_t)P2 : nullptr;
     for (uint32_t k = tid; k < P2; k += kCrowdThreads) {
-      sm.pos[k] = B.pedPos[scp->ped_off + k];
-      sm.vel[k] = B.pedVel[scp->ped_off + k];
-      sm.goalflag[2 * k] = B.goal_bits[2u * (scp->ped_off + k)];
-      sm.goalflag[2 * k + 1] = B.goal_bits[2u * (scp->ped_off + k) + 1u];
+      sm.pos[k] = rec_pv ? rec_pv[k] : B.pedPos[scp->ped_off + k];
+      sm.vel[k] = rec_pv ? rec_pv[P2 + k] : B.pedVel[scp->ped_off + k];
+      sm.goalflag[2 * k] = rec_gf ? rec_gf[2 * k] : B.goal_bits[2u * (scp->ped_off + k)];
+      sm.goalflag[2 * k + 1] = rec_gf ? rec_gf[2 * k + 1] : B.goal_bits[2u * (scp->ped_off + k) + 1u];
       for (uint32_t w = 0; w < (uint32_t)kCrowdWarps; ++w)
         sm.frc[w * P2 + k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -258,7 +314,18 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
     float4 *myrow = sm.frc + warp * P2;
     int steps_done = 0;
     bool collided = false;
-    for (int i = 0; i < S_eff; ++i) {
+    if (rec_in) { // the shared path's bookkeeping at this item's fork point
+      const int alive_in = reinterpret_cast<const int *>(rec_in)[2];
+      if (!alive_in) {
+        collided = true;
+        steps_done = reinterpret_cast<const int *>(rec_in)[3];
+      } else {
+        social_work = *reinterpret_cast<const double *>(rec_in);
+      }
+    }
+    const int i_end = collided ? 0 : min(S_eff, n_run);
+    int written = s0; // writer items: last step count whose record holds a live state
+    for (int i = s0; i < i_end; ++i) {
       // robot as the SFM sees it during computeForces of this step (previous pose)
       const float prx = (i == 0) ? scp->ax : (float)(sm.rx[i] - base_x);
       const float pry = (i == 0) ? scp->ay : (float)(sm.ry[i] - base_y);
@@ -459,6 +526,35 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
         collided = true;
         break;
       }
+      if (writer) { // the path's state after i + 1 steps
+        uint8_t *rec = rec_out + (size_t)(i + 1) * B.share.rec_bytes;
+        float4 *pv = reinterpret_cast<float4 *>(rec + 16);
+        uint8_t *gf = rec + 16 + 32u * (size_t)P2;
+        for (uint32_t k = tid; k < P2; k += kCrowdThreads) {
+          pv[k] = sm.pos[k];
+          pv[P2 + k] = sm.vel[k];
+          gf[2 * k] = sm.goalflag[2 * k];
+          gf[2 * k + 1] = sm.goalflag[2 * k + 1];
+        }
+        if (tid == 0) {
+          *reinterpret_cast<double *>(rec) = social_work;
+          reinterpret_cast<int *>(rec)[2] = 1;
+          reinterpret_cast<int *>(rec)[3] = i + 1;
+        }
+        written = i + 1;
+      }
+    }
+    if (writer) {
+      // step counts the path did not reach alive: a collision kills every descendant; an illegal pose is seen
+      // by the descendants' own footprint check (same poses), they only must not read a stale record
+      if (tid == 0)
+        for (int k = written + 1; k <= (int)B.share.kmax; ++k) {
+          uint8_t *rec = rec_out + (size_t)k * B.share.rec_bytes;
+          *reinterpret_cast<double *>(rec) = social_work;
+          reinterpret_cast<int *>(rec)[2] = collided ? 0 : 1;
+          reinterpret_cast<int *>(rec)[3] = collided ? steps_done : S_eff;
+        }
+      continue; // shared paths have no cost of their own
     }
 
     // ---- terminal costs (sfw_planner.cpp:643-675) -----------------------------------------------
@@ -588,13 +684,13 @@ cudaError_t sfw_crowd_prepare(size_t smem_bytes, int *blocks_per_sm) {
 }
 
 cudaError_t sfw_launch_crowd(const SfwBatchDev &B, unsigned int *work_counter, uint32_t grid, size_t smem_bytes,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, bool with_argmin) {
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), stream);
   if (e != cudaSuccess)
     return e;
   sfw_score_crowd<<<grid, kCrowdThreads, smem_bytes, stream>>>(B, work_counter);
   e = cudaGetLastError();
-  if (e != cudaSuccess)
+  if (e != cudaSuccess || !with_argmin)
     return e;
   sfw_argmin_kernel<<<B.n_scenes, 256, 0, stream>>>(B);
   return cudaGetLastError();

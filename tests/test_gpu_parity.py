@@ -453,3 +453,29 @@ def test_prefix_sharing_is_bit_identical(name, n_scenes):
     assert np.array_equal(best_on, best_off)
     assert pts_on == pts_off
     print(name, k_on, "valid", float((costs_on >= 0).mean()))
+
+
+def test_prefix_sharing_crowd_kernel_is_bit_identical():
+    """The block-per-trajectory kernel shares rollout prefixes the same way (records = pedestrian state +
+    social work + collision bookkeeping; rollout and footprint are recomputed per item)."""
+    from social_force_window_planner_b200.scorer import Scorer
+    wl = dataclasses.replace(S.WORKLOADS["C2"], n_v=64, n_w=64, steps=40, n_peds=200, ped_r_max=7.0)
+    sc = S.make_scene(wl, 1)
+    p = wl.params()
+    lin, ang = wl.sample_arrays()
+    s2 = Scorer(0)
+    try:
+        costs_on, best_on = s2.score(p, [sc], lin, ang)
+        k_on = s2.last_kernel
+        n_on = [s2.trajectory_points(0, i)[1] for i in (1, 2000, 4095)]
+        s2.set_prefix_sharing(False)
+        costs_off, best_off = s2.score(p, [sc], lin, ang)
+        k_off = s2.last_kernel
+        n_off = [s2.trajectory_points(0, i)[1] for i in (1, 2000, 4095)]
+    finally:
+        s2.close()
+    assert k_on == "sfw_score_crowd,share" and k_off == "sfw_score_crowd", (k_on, k_off)
+    assert np.array_equal(costs_on, costs_off) and np.array_equal(best_on, best_off) and n_on == n_off
+    frac = float((costs_on >= 0).mean())
+    assert 0.02 < frac < 0.98, frac  # collisions and survivors both present: dead records are exercised
+    _spot_check(p, sc, lin, ang, costs_on[0], [5, 700, 2080, 4000])
