@@ -444,19 +444,29 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   double sh_mean_s0 = 0.0;
   if (share_candidate) {
     const int kcap = std::min(num_steps - 1, 96);
-    auto ramp = [kcap](double target, double v0, double a_dt, uint16_t &k_out, uint8_t &dir_out) {
-      double vi = v0;
+    // the saturated ramps are the same for every row / column of a scene: build them once per scene (the
+    // additions are the kernel's own, sequentially rounded), then count how far each target lets them run
+    std::vector<double> up(kcap + 1), dn(kcap + 1);
+    auto build = [&](double v0, double a_dt) {
+      up[0] = dn[0] = v0;
+      for (int k = 1; k <= kcap; ++k) {
+        up[k] = up[k - 1] + a_dt;
+        dn[k] = dn[k - 1] - a_dt;
+      }
+    };
+    auto ramp = [&](double target, double v0, double a_dt, uint16_t &k_out, uint8_t &dir_out) {
+      const bool rising = (target - v0) >= 0.0;
       int k = 0;
-      const bool up = (target - vi) >= 0.0;
-      while (k < kcap && a_dt > 0.0) {
-        const double t = up ? vi + a_dt : vi - a_dt;
-        if (up ? !(target >= t) : !(target <= t))
-          break;
-        vi = t;
-        ++k;
+      if (a_dt > 0.0) {
+        if (rising)
+          while (k < kcap && target >= up[k + 1])
+            ++k;
+        else
+          while (k < kcap && target <= dn[k + 1])
+            ++k;
       }
       k_out = (uint16_t)k;
-      dir_out = up ? 1 : 0;
+      dir_out = rising ? 1 : 0;
     };
     const double ax_dt = params->max_trans_acc * dt, ath_dt = params->max_rot_acc * dt;
     sh_kv.resize((size_t)n_scenes * n_v);
@@ -464,8 +474,10 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     sh_kw.resize((size_t)n_scenes * n_w);
     sh_dw.resize((size_t)n_scenes * n_w);
     for (uint32_t s = 0; s < n_scenes; ++s) {
+      build(scenes[s].robot.vx, ax_dt);
       for (uint32_t r = 0; r < n_v; ++r)
         ramp(linvels[r], scenes[s].robot.vx, ax_dt, sh_kv[(size_t)s * n_v + r], sh_dv[(size_t)s * n_v + r]);
+      build(scenes[s].robot.vtheta, ath_dt);
       for (uint32_t q = 0; q < n_w; ++q)
         ramp(angvels[q], scenes[s].robot.vtheta, ath_dt, sh_kw[(size_t)s * n_w + q], sh_dw[(size_t)s * n_w + q]);
     }
