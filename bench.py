@@ -211,8 +211,8 @@ def main():
     ap.add_argument("--workload", default="C1")
     ap.add_argument("--ref-rows", type=int, default=16, help="reference arm: sub-grid rows per step")
     ap.add_argument("--ref-cols", type=int, default=32)
-    ap.add_argument("--cpu-rows", type=int, default=48, help="cpu_baseline leg: sub-grid rows")
-    ap.add_argument("--cpu-cols", type=int, default=48)
+    ap.add_argument("--cpu-rows", type=int, default=96, help="cpu_baseline leg: sub-grid rows")
+    ap.add_argument("--cpu-cols", type=int, default=96)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N > 1: winners exchanged by the scorer's own epilogue over NVLink peer memory (fused) "
