@@ -224,6 +224,13 @@ int sfw_trajectory_points(sfw_ctx *ctx, uint32_t scene, uint32_t sample_index, d
 int sfw_marker_points(sfw_ctx *ctx, uint32_t scene, uint32_t first, uint32_t stride, uint32_t count,
                       double *xyz_out, uint32_t max_points, uint16_t *n_points_out);
 
+/* SFWPlanner::mayIStop (src/sfw_planner.cpp:718-765; unreachable upstream — its call at :637 is commented out —
+ * provided for completeness): brake from (vl_x, vl_y, va) at the acceleration limits of the last sfw_upload and
+ * check the footprint on that scene's costmap at every pose.  *can_stop = 1 when the robot comes to rest without
+ * an illegal footprint, *steps = poses checked. */
+int sfw_may_i_stop(sfw_ctx *ctx, uint32_t scene, double vl_x, double vl_y, double va, double x, double y, double th,
+                   double dt, int32_t *can_stop, uint32_t *steps);
+
 /* ---- the step before the path: laser scan -> obstacle points ----------------------------------
  * SFMSensorInterface::laserCb (reference src/sensor_interface.cpp:103-229): keep the beams that are
  * finite and closer than max_obstacle_dist (:120-122), polar -> cartesian in FLOAT (:124-125; the

@@ -274,6 +274,17 @@ int sfw_ref_markers(const SfwParams *params, const SfwSfmParams *sfm, const SfwS
   return ok ? 1 : 0;
 }
 
+// SFWPlanner::mayIStop of the reference (:718-765; private, unreachable upstream).  Returns 1 / 0.
+int sfw_ref_may_i_stop(const SfwParams *params, const SfwScene *scene, double vl_x, double vl_y, double va, double x,
+                       double y, double th, double dt) {
+  SfwScene sc = *scene;
+  sc.n_peds = 0;
+  sc.n_obstacles = 0;
+  auto rig = make_rig(*params, nullptr, sc);
+  rig->planner->params_.get(rig->node.get(), kName);
+  return rig->planner->mayIStop(vl_x, vl_y, va, x, y, th, dt) ? 1 : 0;
+}
+
 // WorldModel::footprintCost(x,y,theta,spec) of the reference via SFWPlanner::footprintCost (:709).
 double sfw_ref_footprint_cost(const SfwScene *scene, double x, double y, double theta) {
   SfwParams p;

@@ -20,7 +20,7 @@ EXPORTS = [
     "sfw_download", "sfw_sync", "sfw_set_row_slab", "sfw_trajectory_points", "sfw_stream",
     "sfw_device_costs", "sfw_device_best", "sfw_kernel_launches", "sfw_algorithmic_bytes",
     "sfw_last_kernel", "sfw_h2d_bytes", "sfw_d2h_bytes", "sfw_laser_obstacles", "sfw_marker_points", "sfw_exchange_export", "sfw_exchange_connect",
-    "sfw_exchange_sync", "sfw_exchange_fetch", "sfw_exchange_device_buffer", "sfw_set_policy", "sfw_set_prefix_sharing",
+    "sfw_exchange_sync", "sfw_exchange_fetch", "sfw_exchange_device_buffer", "sfw_set_policy", "sfw_set_prefix_sharing", "sfw_may_i_stop",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -83,6 +83,8 @@ def load() -> C.CDLL:
     lib.sfw_marker_points.restype = C.c_int
     lib.sfw_marker_points.argtypes = [_ctx, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _dp, C.c_uint32,
                                       C.POINTER(C.c_uint16)]
+    lib.sfw_may_i_stop.restype = C.c_int
+    lib.sfw_may_i_stop.argtypes = [_ctx, C.c_uint32] + [C.c_double] * 7 + [C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]
     lib.sfw_set_prefix_sharing.restype = C.c_int
     lib.sfw_set_prefix_sharing.argtypes = [_ctx, C.c_int]
     lib.sfw_set_policy.restype = C.c_int

@@ -1146,6 +1146,30 @@ int sfw_marker_points(sfw_ctx *c, uint32_t scene, uint32_t first, uint32_t strid
   return SFW_OK;
 }
 
+int sfw_may_i_stop(sfw_ctx *c, uint32_t scene, double vl_x, double vl_y, double va, double x, double y, double th,
+                   double dt, int32_t *can_stop, uint32_t *steps) {
+  if (!c)
+    return SFW_ERR_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->staged)
+    return fail(c, SFW_ERR_STATE, "sfw_may_i_stop before sfw_upload");
+  if (scene >= c->B.n_scenes || !can_stop || !(dt > 0.0))
+    return fail(c, SFW_ERR_ARG, "sfw_may_i_stop: scene out of range / null output / dt <= 0");
+  CK(c, cudaSetDevice(c->device));
+  int rc = arena_reserve(c, c->sensor_out, 256);
+  if (rc != SFW_OK)
+    return rc;
+  int *d = reinterpret_cast<int *>(c->sensor_out.dev), *h = reinterpret_cast<int *>(c->sensor_out.host);
+  CK(c, sfw_launch_may_i_stop(c->B, scene, vl_x, vl_y, va, x, y, th, dt, d, c->stream));
+  c->launches += 1;
+  CK(c, cudaMemcpyAsync(h, d, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  *can_stop = h[0];
+  if (steps)
+    *steps = (uint32_t)h[1];
+  return SFW_OK;
+}
+
 void *sfw_stream(sfw_ctx *c) { return c ? (void *)c->stream : nullptr; }
 const float *sfw_device_costs(sfw_ctx *c) { return (c && c->staged) ? c->B.costs : nullptr; }
 const void *sfw_device_best(sfw_ctx *c) { return (c && c->staged) ? (const void *)c->B.best : nullptr; }

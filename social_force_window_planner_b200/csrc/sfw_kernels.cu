@@ -725,6 +725,59 @@ extern "C" __global__ void sfw_marker_points_kernel(const __grid_constant__ SfwB
   }
 }
 
+// SFWPlanner::mayIStop (reference src/sfw_planner.cpp:718-765; its only call, :637, is commented out upstream):
+// brake at the acceleration limits from (vl_x, vl_y, va) and check the footprint at every pose until the robot
+// stands.  Faithful to the reference including its argument mix-up: the position update is handed the ANGULAR
+// VELOCITY where the helpers expect the heading (:731-732).  out[0] = 1 can stop / 0 collision, out[1] = steps.
+extern "C" __global__ void sfw_may_i_stop_kernel(const __grid_constant__ SfwBatchDev B, uint32_t scene, double vl_x,
+                                                 double vl_y, double va, double x, double y, double th, double dt,
+                                                 int *out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0)
+    return;
+  const SfwSceneDev *scp = B.scenes + scene;
+  MapView mv;
+  mv.win = nullptr;
+  mv.glob = B.maps + scp->map_off;
+  mv.ox = scp->origin_x;
+  mv.oy = scp->origin_y;
+  mv.res = scp->resolution;
+  mv.rinv = __ddiv_rn(1.0, scp->resolution);
+  mv.sx = scp->size_x;
+  mv.sy = scp->size_y;
+  mv.pitch = B.map_pitch;
+  mv.wx0 = 0;
+  mv.wy0 = 0;
+  mv.wwp = 0;
+  mv.wh = 0;
+  mv.free_bits = nullptr;
+  mv.fw32 = 0;
+  const double2 *fp = B.footprint + scp->fp_off;
+  const double ax_dt = __dmul_rn(B.acc_x, dt), ath_dt = __dmul_rn(B.acc_th, dt);
+  double lvx = vl_x, lvy = vl_y, av = va, xp = x, yp = y, hp = th;
+  int steps = 0, ok = 1;
+  while ((lvx > 0.0 || lvy > 0.0) && steps < 1000000) {
+    lvx = step_velocity(0.0, lvx, ax_dt);
+    lvy = step_velocity(0.0, lvy, ax_dt);
+    av = step_velocity(0.0, av, ath_dt);
+    double sa, ca, sb, cb; // the helpers get `av` as their theta argument (:731-732)
+    sincos(av, &sa, &ca);
+    sincos(__dadd_rn(1.57079632679489661923, av), &sb, &cb);
+    xp = __dadd_rn(xp, __dmul_rn(__dadd_rn(__dmul_rn(lvx, ca), __dmul_rn(lvy, cb)), dt));
+    yp = __dadd_rn(yp, __dmul_rn(__dadd_rn(__dmul_rn(lvx, sa), __dmul_rn(lvy, sb)), dt));
+    hp = __dadd_rn(hp, __dmul_rn(av, dt));
+    double sn, cs;
+    sincos(hp, &sn, &cs);
+    const int fc = footprint_cost(mv, fp, (int)scp->n_fp, xp, yp, sn, cs);
+    ++steps;
+    if (fc < 0) { // footprint_cost folds the reference's "< 0 || >= 254" into -1
+      ok = 0;
+      break;
+    }
+  }
+  out[0] = ok;
+  out[1] = steps;
+}
+
 // ================================================================================================
 // launch wrappers (called from sfw_abi.cu)
 // ================================================================================================
@@ -832,5 +885,11 @@ cudaError_t sfw_launch_marker_points(const SfwBatchDev &B, uint32_t scene, uint3
                                      cudaStream_t stream) {
   sfw_marker_points_kernel<<<(count + 127u) / 128u, 128, 0, stream>>>(B, scene, first, stride, count, max_points,
                                                                     out_xyz, out_n);
+  return cudaGetLastError();
+}
+
+cudaError_t sfw_launch_may_i_stop(const SfwBatchDev &B, uint32_t scene, double vl_x, double vl_y, double va, double x,
+                                  double y, double th, double dt, int *out, cudaStream_t stream) {
+  sfw_may_i_stop_kernel<<<1, 32, 0, stream>>>(B, scene, vl_x, vl_y, va, x, y, th, dt, out);
   return cudaGetLastError();
 }

@@ -23,4 +23,6 @@ cudaError_t sfw_launch_points(const SfwBatchDev &B, uint32_t scene, uint32_t idx
 cudaError_t sfw_launch_marker_points(const SfwBatchDev &B, uint32_t scene, uint32_t first, uint32_t stride,
                                      uint32_t count, uint32_t max_points, double *out_xyz, uint16_t *out_n,
                                      cudaStream_t stream);
+cudaError_t sfw_launch_may_i_stop(const SfwBatchDev &B, uint32_t scene, double vl_x, double vl_y, double va, double x,
+                                  double y, double th, double dt, int *out, cudaStream_t stream);
 #endif

@@ -153,6 +153,12 @@ class Scorer:
         self._check(self._lib.sfw_exchange_fetch(self._ctx, out.ctypes.data_as(C.POINTER(SfwBest))))
         return out
 
+    def may_i_stop(self, scene: int, vl_x, vl_y, va, x, y, th, dt):
+        """``sfw_may_i_stop`` (SFWPlanner::mayIStop, reference src/sfw_planner.cpp:718-765): (can_stop, steps)."""
+        ok, steps = C.c_int32(0), C.c_uint32(0)
+        self._check(self._lib.sfw_may_i_stop(self._ctx, scene, vl_x, vl_y, va, x, y, th, dt, C.byref(ok), C.byref(steps)))
+        return bool(ok.value), int(steps.value)
+
     # -- the step before the path: laser scans -> obstacle points ----------------------------------
     def laser_obstacles(self, scans, max_obstacle_dist: float = 3.0, person_radius: float = 0.35):
         """``sfw_laser_obstacles`` (SFMSensorInterface::laserCb, reference src/sensor_interface.cpp:103-229).

@@ -128,6 +128,8 @@ def ref():
         lib.sfw_ref_markers.argtypes = [C.POINTER(SfwParams), C.POINTER(SfwSfmParams), C.POINTER(SfwScene), _dp,
                                         C.c_uint32, _dp, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint32),
                                         _dp, C.c_uint32]
+        lib.sfw_ref_may_i_stop.restype = C.c_int
+        lib.sfw_ref_may_i_stop.argtypes = [C.POINTER(SfwParams), C.POINTER(SfwScene)] + [C.c_double] * 7
         lib.sfw_ref_default_samples.restype = C.c_int
         lib.sfw_ref_default_samples.argtypes = [C.c_double, C.c_double, _dp, _dp]
         _ref = lib

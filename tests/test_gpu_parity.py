@@ -479,3 +479,22 @@ def test_prefix_sharing_crowd_kernel_is_bit_identical():
     frac = float((costs_on >= 0).mean())
     assert 0.02 < frac < 0.98, frac  # collisions and survivors both present: dead records are exercised
     _spot_check(p, sc, lin, ang, costs_on[0], [5, 700, 2080, 4000])
+
+
+def test_may_i_stop_matches_reference(scorer):
+    """sfw_may_i_stop against what the reference's own (private, unreachable) SFWPlanner::mayIStop returned on
+    the hazards scene (tests/golden/may_i_stop_golden.json, from oracle/_ref)."""
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "may_i_stop_golden.json")))
+    p, sc, lin, ang = G.CASES["c0_hazards_40steps"]()
+    scorer.upload(p, [sc], lin, ang)
+    seen = set()
+    for g in gold:
+        ok, steps = scorer.may_i_stop(0, *g["args"], g["dt"])
+        assert int(ok) == g["can_stop"], g
+        seen.add(g["can_stop"])
+        if g["args"][0] > 0 and ok:  # braking from v at 1 m/s^2 takes ceil(v / (a dt)) steps (+1 when the
+            n = int(np.ceil(g["args"][0] / (p.max_trans_acc * g["dt"]) - 1e-9))  # subtractions leave a residue)
+            assert steps in (n, n + 1), (g, steps)
+    assert seen == {0, 1}

@@ -93,3 +93,20 @@ def test_closed_form_cost_empty_scene():
     dth = abs(float(mn + np.fmod(f(val - mn), f(mx - mn)))) / math.pi
     want = p.vel_weight * abs(p.max_vel_x - v) / p.max_vel_x + p.distance_weight * d2 + p.angle_weight * dth
     assert abs(costs[0] - want) < 1e-9 * want
+
+
+def test_may_i_stop_golden_is_what_the_reference_does():
+    import ctypes as C
+    import json
+    import os
+    import pytest
+    import oracle_lib as ol
+    from social_force_window_planner_b200._abi import SceneArray
+    if not ol.have_ref():
+        pytest.skip("oracle/_ref not built")
+    import golden_cases as G
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "may_i_stop_golden.json")))
+    p, sc, lin, ang = G.CASES["c0_hazards_40steps"]()
+    sa = SceneArray([sc])
+    for g in gold:
+        assert ol.ref().sfw_ref_may_i_stop(C.byref(p), sa.ptr(0), *g["args"], g["dt"]) == g["can_stop"]
