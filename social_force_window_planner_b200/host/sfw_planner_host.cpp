@@ -172,6 +172,19 @@ std::vector<Point2D> SFWPlanner::trajectoryPoints(uint32_t sample_index) {
   return out;
 }
 
+bool SFWPlanner::mayIStop(double vl_x, double vl_y, double va, double x, double y, double th, double dt) {
+  if (!ctx_ || !staged_) {
+    error_ = "mayIStop: no scored tick yet";
+    return false;
+  }
+  int32_t ok = 0;
+  if (sfw_may_i_stop(ctx_, 0, vl_x, vl_y, va, x, y, th, dt, &ok, nullptr) != SFW_OK) {
+    error_ = sfw_last_error(ctx_);
+    return false;
+  }
+  return ok != 0;
+}
+
 std::vector<Marker> SFWPlanner::getMarkerArray() {
   std::vector<Marker> out;
   const size_t n = linvels_.size() * angvels_.size();

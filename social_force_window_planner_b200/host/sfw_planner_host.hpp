@@ -114,6 +114,10 @@ public:
   // sample with the rollout's recorded points (one sfw_marker_points launch), red = rejected, blue = valid,
   // green + raised to z = 0.1 = the chosen one; the skipped (0,0) sample keeps the initial colour, no points
   std::vector<Marker> getMarkerArray();
+  // reference sfw_planner.hpp:348 / sfw_planner.cpp:718-765 (never called upstream): can the robot brake to a
+  // stop from (vl_x, vl_y, va) at pose (x, y, th) without an illegal footprint?  Uses the scene of the last
+  // scored tick; false (with lastError set) before any tick.
+  bool mayIStop(double vl_x, double vl_y, double va, double x, double y, double th, double dt);
   std::vector<Point2D> trajectoryPoints(uint32_t sample_index);
 
   // introspection for tests
