@@ -26,6 +26,16 @@ with torch.cuda.stream(st):
     print(name, "kernel ms", np.median(ts), "traj/s %.3e" % (n / (np.median(ts) * 1e-3)), s.last_kernel)
     costs, best = s.download()
     print("valid", (costs >= 0).sum(), "of", costs.size, "best", best[0])
+    from social_force_window_planner_b200._abi import SceneArray
+    sa = SceneArray(scs)  # marshalled once: the timed call is the C ABI call with host buffers
+    s.score(p, sa, lin, ang, want_costs=True)
     t0 = time.time()
-    for _ in range(5): s.score(p, scs, lin, ang, want_costs=True)
+    for _ in range(5): s.score(p, sa, lin, ang, want_costs=True)
     print("e2e ms", (time.time() - t0) / 5 * 1e3)
+    t0 = time.time()
+    for _ in range(5): s.upload(p, sa, lin, ang); s.sync()
+    print("  upload+sync ms", (time.time() - t0) / 5 * 1e3)
+    s.run(); s.sync()
+    t0 = time.time()
+    for _ in range(5): s.download()
+    print("  download ms", (time.time() - t0) / 5 * 1e3)
