@@ -73,12 +73,12 @@ PathMsg SFWPlannerNode::transformGlobalPlan(const PoseStampedMsg &rpose) {
   if (!transformPose(global_plan_.frame_id, rpose, robot_pose))
     throw PlannerException("Unable to transform robot pose into global plan's frame");
 
-  // We'll discard points on the plan that are outside the local costmap
+  // plan poses farther than half the costmap's larger side cannot matter to the local planner
   const double max_costmap_dim = std::max(costmap_->size_x, costmap_->size_y);
   const double max_transform_dist = max_costmap_dim * costmap_->resolution / 2.0;
   auto dist = [&robot_pose](const Pose2D &p) { return std::hypot(robot_pose.pose.x - p.x, robot_pose.pose.y - p.y); };
 
-  // First find the closest pose on the path to the robot (min_by: first minimum wins)
+  // nearest plan pose to the robot (the reference's min_by keeps the FIRST minimum)
   auto transformation_begin = global_plan_.poses.begin();
   {
     double lowest = dist(*transformation_begin);
@@ -90,7 +90,7 @@ PathMsg SFWPlannerNode::transformGlobalPlan(const PoseStampedMsg &rpose) {
       }
     }
   }
-  // Find points definitely outside of the costmap so we won't transform them.
+  // first pose after it that lies beyond that distance: the cut
   auto transformation_end = std::find_if(transformation_begin, global_plan_.poses.end(),
                                          [&](const Pose2D &p) { return dist(p) > max_transform_dist; });
 
@@ -102,7 +102,7 @@ PathMsg SFWPlannerNode::transformGlobalPlan(const PoseStampedMsg &rpose) {
   }
   transformed_plan.frame_id = global_frame_;
 
-  // path pruning
+  // drop what lies behind the nearest pose from the stored plan
   global_plan_.poses.erase(global_plan_.poses.begin(), transformation_begin);
   transformed_plan_ = transformed_plan;
   if (transformed_plan.poses.empty())

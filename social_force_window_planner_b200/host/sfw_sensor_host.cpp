@@ -9,7 +9,7 @@ namespace social_force_window_planner {
 
 SFMSensorInterface::SFMSensorInterface(const InterfaceParams &params, int device)
     : iface_params_(params), device_(device) {
-  // Initialize SFM. Just one agent (the robot)  (reference :31-37)
+  // the agent list starts with the robot alone (reference :31-37)
   agents_.resize(1);
   agents_[0].desiredVelocity = iface_params_.max_robot_vel_x_;
   agents_[0].radius = iface_params_.robot_radius_;
@@ -157,7 +157,7 @@ void SFMSensorInterface::peopleCb(const PeopleMsg &people) {
     ag.desiredVelocity = iface_params_.people_velocity_;
     agents.push_back(ag);
   }
-  // Fill the obstacles of the agents (:513-518)
+  // every agent carries the current obstacle list (:513-518)
   obs_mutex_.lock();
   std::vector<Point2D> obs_points = obstacles_;
   obs_mutex_.unlock();
@@ -183,7 +183,7 @@ void SFMSensorInterface::odomCb(const OdometryMsg &odom) {
   agent.yaw = odom.yaw;
   agent.linearVelocity = std::sqrt(odom.vx * odom.vx + odom.vy * odom.vy);
   agent.angularVelocity = odom.wz;
-  // The velocity in the odom messages is in the robot local frame!!! (:565-575)
+  // odometry twist is expressed in the ROBOT frame and stored as is (:565-575)
   agent.velocity = Point2D{odom.vx, odom.vy};
   agents_mutex_.lock();
   agents_[0] = agent;
