@@ -439,7 +439,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
                                num_steps >= 8;
   std::vector<uint16_t> sh_kv, sh_kw;
   std::vector<uint8_t> sh_dv, sh_dw;
-  std::vector<uint32_t> sh_perm, sh_rperm;
+  std::vector<uint32_t> sh_perm, sh_rperm, sh_sperm;
   uint32_t sh_kmax = 0;
   double sh_mean_s0 = 0.0;
   if (share_candidate) {
@@ -508,6 +508,26 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
       }
     }
     sh_mean_s0 = cnt ? acc / (double)cnt : 0.0;
+    if ((uint64_t)n_v * n_w <= 65536 && (double)n_scenes * n_v * n_w >= 2.5 * c->sm_count * 384.0) {
+      // (only when the batch can pass the several-waves test of the sharing decision below)
+      // small enough to sort every sample by its fork step (counting sort, scene 0's tables): warps of equal
+      // fork step whatever the aspect of the grid
+      std::vector<uint32_t> bucket(sh_kmax + 2, 0);
+      for (uint32_t r = 0; r < n_v; ++r)
+        for (uint32_t q = 0; q < n_w; ++q)
+          ++bucket[std::max(sh_kv[r], sh_kw[q]) + 1u];
+      for (uint32_t k = 1; k < bucket.size(); ++k)
+        bucket[k] += bucket[k - 1];
+      sh_sperm.resize((size_t)n_v * n_w);
+      double tot = 0.0;
+      for (uint32_t r = 0; r < n_v; ++r)
+        for (uint32_t q = 0; q < n_w; ++q) {
+          const uint32_t k = std::max(sh_kv[r], sh_kw[q]);
+          sh_sperm[bucket[k]++] = r * n_w + q;
+          tot += k;
+        }
+      sh_mean_s0 = tot / ((double)n_v * n_w);
+    }
   }
 
   // ---- staged window: everything the footprint can touch ------------------------------------
@@ -597,6 +617,8 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   off = align_up(off + 4 * sh_perm.size(), kAlign);
   const size_t o_srperm = off;
   off = align_up(off + 4 * sh_rperm.size(), kAlign);
+  const size_t o_ssperm = off;
+  off = align_up(off + 4 * sh_sperm.size(), kAlign);
   const size_t o_maps = off;
   off = align_up(off + slot * n_scenes, kAlign);
   const size_t in_bytes = off;
@@ -624,6 +646,8 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     memcpy(h + o_sdw, sh_dw.data(), sh_dw.size());
     memcpy(h + o_sperm, sh_perm.data(), 4 * sh_perm.size());
     memcpy(h + o_srperm, sh_rperm.data(), 4 * sh_rperm.size());
+    if (!sh_sperm.empty())
+      memcpy(h + o_ssperm, sh_sperm.data(), 4 * sh_sperm.size());
   }
   memcpy(h + o_lin, linvels, 8 * (size_t)n_v);
   memcpy(h + o_ang, angvels, 8 * (size_t)n_w);
@@ -855,6 +879,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
       B.share.dirw = dv + o_sdw;
       B.share.col_perm = reinterpret_cast<const uint32_t *>(dv + o_sperm);
       B.share.row_perm = reinterpret_cast<const uint32_t *>(dv + o_srperm);
+      B.share.sample_perm = sh_sperm.empty() ? nullptr : reinterpret_cast<const uint32_t *>(dv + o_ssperm);
       B.share.scene_stride = (uint64_t)paths * (sh_kmax + 1u) * rec;
       B.share.rec_bytes = rec;
       B.share.kmax = sh_kmax;

@@ -88,6 +88,9 @@ struct SfwShareDev {
   // row, consecutive warps = consecutive rows of row_perm (sorted by kv) on the same 32 columns -> the lanes of a
   // warp and the warps of a block start (and finish) together
   const uint32_t *col_perm, *row_perm;
+  // grids of at most 65 536 samples: every sample sorted by its fork step (scene 0's tables), so that a warp is
+  // 32 samples that fork together whatever the grid's aspect (nullptr: use the row / column walk above)
+  const uint32_t *sample_perm;
   uint64_t scene_stride;
   uint32_t rec_bytes, kmax;
   uint32_t mode, pad0;      // 0 off, 1 / 2 path writers, 3 reader

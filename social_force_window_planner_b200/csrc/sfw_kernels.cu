@@ -203,7 +203,11 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
     if (share_mode == 3u) {
       if (in_range) {
         uint32_t r, c;
-        if ((n_w & 31u) == 0u) { // warp-major walk: 32 sorted columns x sorted rows
+        if (H.sample_perm) { // samples sorted by fork step
+          const uint32_t sidx = H.sample_perm[idx];
+          r = sidx / n_w;
+          c = sidx - r * n_w;
+        } else if ((n_w & 31u) == 0u) { // warp-major walk: 32 sorted columns x sorted rows
           const uint32_t w = idx >> 5, chunk = w / B.n_v;
           r = H.row_perm[w - chunk * B.n_v];
           c = H.col_perm[chunk * 32u + (idx & 31u)];
