@@ -344,6 +344,8 @@ def main():
             total_ms = float(t.item())
         costs_dev, best_dev = scorer.download()
         kernel_name = scorer.last_kernel
+        shared_steps = scorer.shared_prefix_steps
+        shared_kmax = min(wl.steps, 2.0 * shared_steps)  # estimate of a shared path's length (the longest ramp)
         algo_bytes = scorer.algorithmic_bytes
 
         # ---- end-to-end arm: host buffers in, host cost vector + winner out, every step ----------------
@@ -395,8 +397,12 @@ def main():
         # pedestrian pair and every robot-pedestrian pair once per step (2 rsqrt + 2 ex2, + 1 sqrt for the
         # social-work magnitude of the robot pairs), 2 per obstacle term (rsqrt, ex2), 2 rsqrt per
         # pedestrian update (goal direction, speed cap), one extra robot-pedestrian pass after the last step.
+        # With rollout prefix sharing a sample does not execute its first `shared` steps (mean over the grid, from
+        # the library); the shared paths themselves add 2 (n_v + n_w) + 4 path-prefixes, counted too.
         P_, M_, S_ = wl.n_peds, wl.n_obstacles, wl.steps
-        mufu_exec = S_ * (4 * (P_ * (P_ - 1) // 2 + P_) + P_ + 2 * (P_ + 1) * M_ + 2 * P_) + 5 * P_
+        per_step = 4 * (P_ * (P_ - 1) // 2 + P_) + P_ + 2 * (P_ + 1) * M_ + 2 * P_
+        path_steps = (2 * (wl.n_v + wl.n_w) + 4) * shared_kmax / wl.samples if shared_steps > 0 else 0.0
+        mufu_exec = (S_ - shared_steps + path_steps) * per_step + 5 * P_
         mufu_per_s = mufu_exec * wl.samples / (k_ms * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -412,6 +418,11 @@ def main():
                          "nccl": "NCCL all-gather of the 32-byte winner records after the kernel",
                          "none": "single GPU"}[exchange],
             "kernel": kernel_name, "kernel_ms": k_ms, "wall_s_timed_region": t_wall,
+            "prefix_sharing": {"mean_shared_steps": shared_steps, "of_steps": wl.steps,
+                               "launches_per_tick": int(launches) // max(args.steps, 1),
+                               "note": "samples whose velocity ramps are still saturated start from the record of a "
+                                       "shared path (bit-identical to the unshared run); kernel_ms covers the path "
+                                       "launches and the sample launch"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo_bytes),
@@ -420,8 +431,9 @@ def main():
                       "mufu_executed_per_s": mufu_per_s, "mufu_peak_per_s": 148 * 16 * f_sm,
                       "mufu_frac": mufu_per_s / (148 * 16 * f_sm),
                       "model": "reference work (SURVEY.md 8d): S*[N(N-1)+(N-1)] pair + S*N*M obstacle evaluations per "
-                               "trajectory; MUFU count: what the kernel executes (each unordered pair once, 4 MUFU; "
-                               "obstacle term 2 MUFU) against 16 MUFU/clk/SM at the sampled SM clock"},
+                               "trajectory (all S steps, as the reference computes them); MUFU count: what the kernels "
+                               "execute (each unordered pair once, 4 MUFU; obstacle term 2 MUFU; steps taken from a shared "
+                               "path are not counted) against 16 MUFU/clk/SM at the sampled SM clock"},
             "clocks": ck,
             "winner": {"valid": int(best_dev[0]["valid"]), "index": int(best_dev[0]["index"]),
                        "v": float(best_dev[0]["v"]), "w": float(best_dev[0]["w"]), "cost": float(best_dev[0]["cost"])},

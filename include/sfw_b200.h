@@ -203,7 +203,9 @@ int sfw_set_policy(sfw_ctx *ctx, int policy);
 /* Rollout prefix sharing (on by default; applies from the next sfw_upload).  With acceleration limits, samples
  * whose velocity is still ramping at the full +-a*dt per step are identical for their first steps; on dense
  * multi-wave grids the library simulates those shared prefixes once and starts every sample from the state of
- * its fork point.  The cost vector is bit-identical either way (same arithmetic, same order). */
+ * its fork point.  The cost vector is bit-identical either way (same arithmetic, same order).
+ * on: 0 = never, 1 = when the library's cost model says it pays (default), 2 = whenever the staged batch allows
+ * it (grids of >= 1024 samples, >= 8 steps, some saturated ramp; for tests and experiments). */
 int sfw_set_prefix_sharing(sfw_ctx *ctx, int on);
 
 /* Restrict the next sfw_run calls to linvel rows [row_begin, row_end) of every staged scene
@@ -287,6 +289,9 @@ uint64_t sfw_h2d_bytes(const sfw_ctx *ctx);
 uint64_t sfw_d2h_bytes(const sfw_ctx *ctx);
 /* name of the kernel variant the last sfw_run dispatched to (for logs/profiles) */
 const char *sfw_last_kernel(const sfw_ctx *ctx);
+/* rollout prefix sharing of the staged batch: mean number of leading steps a sample takes from a shared path
+ * instead of simulating them itself (0 when sharing is off for this batch) */
+double sfw_shared_prefix_steps(const sfw_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ EXPORTS = [
     "sfw_default_sfm_params", "sfw_score", "sfw_score_batch", "sfw_upload", "sfw_run",
     "sfw_download", "sfw_sync", "sfw_set_row_slab", "sfw_trajectory_points", "sfw_stream",
     "sfw_device_costs", "sfw_device_best", "sfw_kernel_launches", "sfw_algorithmic_bytes",
-    "sfw_last_kernel", "sfw_h2d_bytes", "sfw_d2h_bytes", "sfw_laser_obstacles", "sfw_marker_points", "sfw_exchange_export", "sfw_exchange_connect",
+    "sfw_last_kernel", "sfw_shared_prefix_steps", "sfw_h2d_bytes", "sfw_d2h_bytes", "sfw_laser_obstacles", "sfw_marker_points", "sfw_exchange_export", "sfw_exchange_connect",
     "sfw_exchange_sync", "sfw_exchange_fetch", "sfw_exchange_device_buffer", "sfw_set_policy", "sfw_set_prefix_sharing", "sfw_may_i_stop",
 ]
 
@@ -101,6 +101,8 @@ def load() -> C.CDLL:
     lib.sfw_exchange_device_buffer.argtypes = [_ctx]
     lib.sfw_last_kernel.restype = C.c_char_p
     lib.sfw_last_kernel.argtypes = [_ctx]
+    lib.sfw_shared_prefix_steps.restype = C.c_double
+    lib.sfw_shared_prefix_steps.argtypes = [_ctx]
     return lib
 
 

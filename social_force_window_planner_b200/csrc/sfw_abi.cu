@@ -432,6 +432,60 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     return fail(c, SFW_ERR_UNSUPPORTED, "num_steps %d > 65535", num_steps);
   const double dt = params->sim_time / num_steps; // :527
 
+  // ---- staged window: everything the footprint can touch ------------------------------------
+  double max_lin = 0.0;
+  for (uint32_t i = 0; i < n_v; ++i)
+    max_lin = std::max(max_lin, std::fabs(linvels[i]));
+  uint32_t win_wp = 0, win_h = 0;
+  std::vector<int32_t> wx0(n_scenes), wy0(n_scenes);
+  {
+    int64_t need = 0;
+    bool ok = true;
+    for (uint32_t s = 0; s < n_scenes && ok; ++s) {
+      const SfwScene &sc = scenes[s];
+      double circ = 0.0;
+      for (uint32_t k = 0; k < sc.n_footprint; ++k)
+        circ = std::max(circ, std::hypot(sc.footprint_xy[2 * k], sc.footprint_xy[2 * k + 1]));
+      const double speed = std::hypot(std::max(max_lin, std::fabs(sc.robot.vx)), sc.robot.vy);
+      const double reach = speed * params->sim_time + circ;
+      const double rc_d = std::ceil(reach / sc.resolution) + 2.0;
+      if (!(rc_d < 4096.0)) {
+        ok = false;
+        break;
+      }
+      const int64_t rc = (int64_t)rc_d;
+      const double cxd = std::floor((sc.robot.x - sc.origin_x) / sc.resolution);
+      const double cyd = std::floor((sc.robot.y - sc.origin_y) / sc.resolution);
+      if (!(std::fabs(cxd) < 1e9) || !(std::fabs(cyd) < 1e9)) {
+        ok = false;
+        break;
+      }
+      // TMA (measured on B200): the innermost start coordinate times the element size must be a
+      // multiple of 16 bytes or the copy traps as an illegal instruction -> floor x0 to 16 cells
+      // and widen the box by the slack.
+      const int64_t x0 = (int64_t)cxd - rc;
+      const int64_t x0a = (x0 >= 0) ? (x0 / 16) * 16 : -(((-x0) + 15) / 16) * 16;
+      wx0[s] = (int32_t)x0a;
+      wy0[s] = (int32_t)((int64_t)cyd - rc);
+      need = std::max<int64_t>(need, 2 * rc + 1);
+    }
+    if (ok && need > 0) {
+      const uint32_t wp = (uint32_t)align_up((size_t)need + 15, 16);
+      if (wp <= 256 && need <= 256 && (size_t)wp * need <= 48 * 1024) {
+        win_wp = wp;
+        win_h = (uint32_t)need;
+      }
+    }
+  }
+
+  // ---- launch plan (block size, kernel family): needed by the sharing decision below ----------
+  const uint32_t samples = n_v * n_w;
+  {
+    const int prc = make_plan(c, n_scenes, samples, maxP, maxM, maxF, win_wp, win_h, num_steps);
+    if (prc != SFW_OK)
+      return prc;
+  }
+
   // ---- rollout prefix sharing: leading saturated updates of every row / column (SfwShareDev) ----
   // Replays the scalar recurrences of step_velocity exactly as the kernel evaluates them (IEEE double add /
   // compare): update k of row r is "saturated" iff the ramp vi +- a*dt does not reach the target yet.
@@ -439,7 +493,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
                                num_steps >= 8;
   std::vector<uint16_t> sh_kv, sh_kw;
   std::vector<uint8_t> sh_dv, sh_dw;
-  std::vector<uint32_t> sh_perm, sh_rperm, sh_sperm;
+  std::vector<uint32_t> sh_perm, sh_rperm, sh_lvl_rows, sh_lvl_cols, sh_chunk_map;
   uint32_t sh_kmax = 0;
   double sh_mean_s0 = 0.0;
   if (share_candidate) {
@@ -494,84 +548,134 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     for (uint32_t r = 0; r < n_v; ++r)
       sh_rperm[r] = r;
     std::stable_sort(sh_rperm.begin(), sh_rperm.end(), [&](uint32_t a, uint32_t b) { return sh_kv[a] < sh_kv[b]; });
-    // what a warp saves: the smallest fork step among its 32 lanes = max(kv[row], min kw of its 32 columns)
-    // (scene 0's tables)
-    double acc = 0.0;
-    uint64_t cnt = 0;
-    for (uint32_t q0 = 0; q0 < n_w; q0 += 32) {
-      uint32_t mkw = 0xffffffffu;
-      for (uint32_t q = q0; q < std::min(q0 + 32, n_w); ++q)
-        mkw = std::min<uint32_t>(mkw, sh_kw[sh_perm[q]]);
-      for (uint32_t r = 0; r < n_v; ++r) {
-        acc += std::max<uint32_t>(sh_kv[r], mkw);
-        ++cnt;
-      }
-    }
-    sh_mean_s0 = cnt ? acc / (double)cnt : 0.0;
-    if ((uint64_t)n_v * n_w <= 65536 && (double)n_scenes * n_v * n_w >= 2.5 * c->sm_count * 384.0) {
-      // (only when the batch can pass the several-waves test of the sharing decision below)
-      // small enough to sort every sample by its fork step (counting sort, scene 0's tables): warps of equal
-      // fork step whatever the aspect of the grid
-      std::vector<uint32_t> bucket(sh_kmax + 2, 0);
+    // every sample's own fork step (scene 0's tables)
+    {
+      std::vector<double> hv(sh_kmax + 1u, 0.0), hw(sh_kmax + 1u, 0.0);
       for (uint32_t r = 0; r < n_v; ++r)
-        for (uint32_t q = 0; q < n_w; ++q)
-          ++bucket[std::max(sh_kv[r], sh_kw[q]) + 1u];
-      for (uint32_t k = 1; k < bucket.size(); ++k)
-        bucket[k] += bucket[k - 1];
-      sh_sperm.resize((size_t)n_v * n_w);
+        hv[sh_kv[r]] += 1.0;
+      for (uint32_t q = 0; q < n_w; ++q)
+        hw[sh_kw[q]] += 1.0;
       double tot = 0.0;
-      for (uint32_t r = 0; r < n_v; ++r)
-        for (uint32_t q = 0; q < n_w; ++q) {
-          const uint32_t k = std::max(sh_kv[r], sh_kw[q]);
-          sh_sperm[bucket[k]++] = r * n_w + q;
-          tot += k;
-        }
+      for (uint32_t a = 0; a <= sh_kmax; ++a)
+        for (uint32_t b = 0; b <= sh_kmax; ++b)
+          tot += hv[a] * hw[b] * (double)std::max(a, b);
       sh_mean_s0 = tot / ((double)n_v * n_w);
+      // rows / columns that fork before step k (scene 0)
+      sh_lvl_rows.assign(sh_kmax + 2u, 0u);
+      sh_lvl_cols.assign(sh_kmax + 2u, 0u);
+      for (uint32_t k = 0; k <= sh_kmax; ++k) {
+        sh_lvl_rows[k + 1u] = sh_lvl_rows[k] + (uint32_t)hv[k];
+        sh_lvl_cols[k + 1u] = sh_lvl_cols[k] + (uint32_t)hw[k];
+      }
     }
   }
-
-  // ---- staged window: everything the footprint can touch ------------------------------------
-  double max_lin = 0.0;
-  for (uint32_t i = 0; i < n_v; ++i)
-    max_lin = std::max(max_lin, std::fabs(linvels[i]));
-  uint32_t win_wp = 0, win_h = 0;
-  std::vector<int32_t> wx0(n_scenes), wy0(n_scenes);
-  {
-    int64_t need = 0;
-    bool ok = true;
-    for (uint32_t s = 0; s < n_scenes && ok; ++s) {
-      const SfwScene &sc = scenes[s];
-      double circ = 0.0;
-      for (uint32_t k = 0; k < sc.n_footprint; ++k)
-        circ = std::max(circ, std::hypot(sc.footprint_xy[2 * k], sc.footprint_xy[2 * k + 1]));
-      const double speed = std::hypot(std::max(max_lin, std::fabs(sc.robot.vx)), sc.robot.vy);
-      const double reach = speed * params->sim_time + circ;
-      const double rc_d = std::ceil(reach / sc.resolution) + 2.0;
-      if (!(rc_d < 4096.0)) {
-        ok = false;
-        break;
-      }
-      const int64_t rc = (int64_t)rc_d;
-      const double cxd = std::floor((sc.robot.x - sc.origin_x) / sc.resolution);
-      const double cyd = std::floor((sc.robot.y - sc.origin_y) / sc.resolution);
-      if (!(std::fabs(cxd) < 1e9) || !(std::fabs(cyd) < 1e9)) {
-        ok = false;
-        break;
-      }
-      // TMA (measured on B200): the innermost start coordinate times the element size must be a
-      // multiple of 16 bytes or the copy traps as an illegal instruction -> floor x0 to 16 cells
-      // and widen the box by the slack.
-      const int64_t x0 = (int64_t)cxd - rc;
-      const int64_t x0a = (x0 >= 0) ? (x0 / 16) * 16 : -(((-x0) + 15) / 16) * 16;
-      wx0[s] = (int32_t)x0a;
-      wy0[s] = (int32_t)((int64_t)cyd - rc);
-      need = std::max<int64_t>(need, 2 * rc + 1);
+  // ---- worth it?  Sharing removes the first max(kv, kw) steps of every sample and costs two latency-bound
+  // path launches of kmax steps each.  Cost model from scripts/share_probe.py / latency_probe.py (us).
+  bool share_on = false, share_dealt = false;
+  uint32_t share_warp = 0; // bit 0 / 1: launch 1 / 2 uses the warp-per-path writer
+  uint32_t share_rec = 0;
+  size_t share_need = 0;
+  const uint32_t share_paths = 4u + 2u * n_w + 2u * n_v;
+  if (share_candidate && sh_kmax >= 2) {
+    const bool crowd = c->plan.crowd;
+    const double P = (double)maxP, S = (double)num_steps;
+    const double total = (double)n_scenes * samples;
+    const uint32_t P2max = (maxP + 1u) / 2u;
+    const double resident = crowd ? (double)c->plan.grid : (double)c->sm_count * c->plan.k * c->plan.T;
+    // thread-per-trajectory: throughput cost of a trajectory-step / one step of a lone warp;
+    // block-per-trajectory: a trajectory-step at full occupancy / one step of one block
+    const double t_ts_ns = crowd ? 0.2 + 0.00085 * P * P : 0.1 + 0.017 * P + 0.0008 * P * P;
+    const double t_lat_us = crowd ? 2.0 + 0.00025 * P * P : 1.3 + 0.25 * P + 0.028 * P * P;
+    const bool single = !crowd && total <= resident;
+    const double mean_s0 = sh_mean_s0;
+    double saved_us, margin;
+    if (single) {
+      // one wave: T = c1 (N + 1.5) per step with N warps per scheduler and c1 = t_lat / 2.5 (profiles/README.md);
+      // the plain launch ends with its fullest scheduler, the dealt one (below) with the average
+      const double N = (double)c->plan.T * c->plan.k / 128.0, c1 = t_lat_us / 2.5;
+      saved_us = c1 * (S * (std::ceil(N) + 1.5) - (S - mean_s0) * (N + 1.5));
+      margin = 1.5;
+    } else {
+      saved_us = total * mean_s0 * t_ts_ns * 1e-3;
+      margin = crowd ? 2.0 : 1.5;
     }
-    if (ok && need > 0) {
-      const uint32_t wp = (uint32_t)align_up((size_t)need + 15, 16);
-      if (wp <= 256 && need <= 256 && (size_t)wp * need <= 48 * 1024) {
-        win_wp = wp;
-        win_h = (uint32_t)need;
+    // the writers (thread-per-trajectory family): a thread per path (step = 2 + 0.94 P + 0.0027 P^2 us, measured
+    // 11.7 / 23 us at 10 / 21 pedestrians) or, without pedestrian groups, a warp per path (3 + 0.16 P us, and
+    // ~20 % more per extra warp on the scheduler); chosen per launch
+    double cost_us;
+    if (crowd) {
+      const double path_waves = std::ceil((double)n_scenes * share_paths / resident);
+      cost_us = (1.0 + path_waves) * sh_kmax * t_lat_us + 30.0;
+    } else {
+      const double t_thr = 2.0 + 0.94 * P + 0.0027 * P * P, t_warp = 3.0 + 0.16 * P;
+      const size_t smw = sfw_small_smem_bytes(win_wp, win_h, maxP, maxM, maxF, SFW_PATH_WARP_THREADS);
+      const double per_sm = std::max(1.0, std::min(16.0, std::floor(227.0 * 1024.0 / (double)(smw + 1024))));
+      const double slots = c->sm_count * per_sm;
+      auto warp_cost = [&](double blocks) {
+        const double waves = std::ceil(blocks / slots), wps = std::min(per_sm, std::ceil(blocks / c->sm_count));
+        return sh_kmax * t_warp * waves * (1.0 + 0.2 * (wps - 1.0)) + 20.0;
+      };
+      auto thread_cost = [&](double blocks) { return sh_kmax * t_thr * std::ceil(blocks / slots) + 20.0; };
+      const double paths2 = (double)(share_paths - 4u);
+      double c1 = thread_cost((double)n_scenes), c2 = thread_cost((double)n_scenes * std::ceil(paths2 / 128.0));
+      if (grp_table.empty()) {
+        const double w1 = warp_cost((double)n_scenes);
+        const double w2 = warp_cost((double)n_scenes * std::ceil(paths2 / (SFW_PATH_WARP_THREADS / 32.0)));
+        if (w1 < c1) {
+          c1 = w1;
+          share_warp |= 1u;
+        }
+        if (w2 < c2) {
+          c2 = w2;
+          share_warp |= 2u;
+        }
+      }
+      cost_us = c1 + c2 + 10.0;
+    }
+    share_rec = crowd ? (uint32_t)align_up(16u + 32u * P2max + 2u * P2max, 16)
+                      : (uint32_t)align_up(sizeof(SfwCkptHdr) + 32u * P2max, 16);
+    share_need = (size_t)n_scenes * share_paths * (sh_kmax + 1u) * share_rec;
+    share_on = (saved_us > margin * cost_us || c->share_allowed == 2) && share_need <= ((size_t)8 << 30);
+    share_dealt = share_on && !crowd && total < 2.5 * resident; // few waves: every block gets the same mix
+    if (getenv("SFW_B200_TRACE_SHARING"))
+      fprintf(stderr,
+              "sfw_b200 sharing: %s kernel, %u scenes x %u samples, P=%u S=%d kmax=%u mean fork step %.2f, %s, "
+              "saved %.0f us vs cost %.0f us (%s writers) -> %s\n",
+              crowd ? "block-per-trajectory" : "thread-per-trajectory", n_scenes, samples, maxP, num_steps, sh_kmax,
+              mean_s0, single ? "one wave" : "several waves", saved_us, cost_us,
+              share_warp == 3u ? "warp" : share_warp == 1u ? "warp + thread" : share_warp == 2u ? "thread + warp" : "thread",
+              share_on ? "on" : "off");
+    if (share_dealt) {
+      // One wave: a block-sorted order would leave the blocks of unshortened samples as long as before.  Deal
+      // the fork-sorted 32-sample chunks over (block, scheduler) bins instead -- warp w of a block issues from
+      // scheduler w % 4 -- longest chunks to the bins that hold the fewest warps (448 threads = 14 warps sit
+      // 4/4/3/3 on the schedulers), boustrophedon within a class of equal capacity so that the sums level out.
+      const uint32_t T = c->plan.T, wpb = T / 32u, nchunk = (samples + 31u) / 32u, nblk = c->plan.tiles;
+      struct Bin {
+        uint32_t cap, blk, sch;
+      };
+      std::vector<Bin> bins;
+      bins.reserve((size_t)nblk * 4u);
+      for (uint32_t b = 0; b < nblk; ++b) {
+        const uint32_t warps = std::min(wpb, nchunk - std::min(nchunk, b * wpb));
+        for (uint32_t q = 0; q < 4u; ++q)
+          if (q < warps)
+            bins.push_back({(warps - q + 3u) / 4u, b, q});
+      }
+      std::stable_sort(bins.begin(), bins.end(), [](const Bin &a, const Bin &b) { return a.cap < b.cap; });
+      sh_chunk_map.assign((size_t)nblk * wpb, 0u);
+      uint32_t ch = 0; // chunks in ascending fork step = longest first
+      for (size_t b0 = 0; b0 < bins.size();) {
+        size_t b1 = b0;
+        while (b1 < bins.size() && bins[b1].cap == bins[b0].cap)
+          ++b1;
+        const size_t nb = b1 - b0;
+        for (uint32_t slot = 0; slot < bins[b0].cap; ++slot)
+          for (size_t i = 0; i < nb; ++i, ++ch) {
+            const Bin &bn = bins[b0 + ((slot & 1u) ? nb - 1 - i : i)];
+            sh_chunk_map[(size_t)bn.blk * wpb + bn.sch + 4u * slot] = ch;
+          }
+        b0 = b1;
       }
     }
   }
@@ -617,8 +721,12 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   off = align_up(off + 4 * sh_perm.size(), kAlign);
   const size_t o_srperm = off;
   off = align_up(off + 4 * sh_rperm.size(), kAlign);
-  const size_t o_ssperm = off;
-  off = align_up(off + 4 * sh_sperm.size(), kAlign);
+  const size_t o_slr = off;
+  off = align_up(off + 4 * sh_lvl_rows.size(), kAlign);
+  const size_t o_slc = off;
+  off = align_up(off + 4 * sh_lvl_cols.size(), kAlign);
+  const size_t o_scm = off;
+  off = align_up(off + 4 * sh_chunk_map.size(), kAlign);
   const size_t o_maps = off;
   off = align_up(off + slot * n_scenes, kAlign);
   const size_t in_bytes = off;
@@ -646,8 +754,10 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     memcpy(h + o_sdw, sh_dw.data(), sh_dw.size());
     memcpy(h + o_sperm, sh_perm.data(), 4 * sh_perm.size());
     memcpy(h + o_srperm, sh_rperm.data(), 4 * sh_rperm.size());
-    if (!sh_sperm.empty())
-      memcpy(h + o_ssperm, sh_sperm.data(), 4 * sh_sperm.size());
+    memcpy(h + o_slr, sh_lvl_rows.data(), 4 * sh_lvl_rows.size());
+    memcpy(h + o_slc, sh_lvl_cols.data(), 4 * sh_lvl_cols.size());
+    if (!sh_chunk_map.empty())
+      memcpy(h + o_scm, sh_chunk_map.data(), 4 * sh_chunk_map.size());
   }
   memcpy(h + o_lin, linvels, 8 * (size_t)n_v);
   memcpy(h + o_ang, angvels, 8 * (size_t)n_w);
@@ -758,10 +868,6 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   c->scene_host.assign(hs, hs + n_scenes);
 
   // ---- outputs -------------------------------------------------------------------------------
-  const uint32_t samples = n_v * n_w;
-  rc = make_plan(c, n_scenes, samples, maxP, maxM, maxF, win_wp, win_h, num_steps);
-  if (rc != SFW_OK)
-    return rc;
   const uint32_t max_tiles = (samples + 31) / 32; // any slab / block size fits
   size_t oo = 0;
   c->off_best = oo;
@@ -842,52 +948,37 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   B.k_gaze = (float)sfm.force_factor_group_gaze;
   B.k_coh = (float)sfm.force_factor_group_coherence;
   B.k_rep = (float)sfm.force_factor_group_repulsion;
-  // ---- prefix sharing: worth it?  It removes mean_s0 of num_steps steps from every warp, and costs two
-  // latency-bound launches of kmax steps each; a launch that fits one wave ends with its slowest block anyway.
+  // ---- prefix sharing decided above: records + tables ----------------------------------------
   c->share_active = false;
-  if (share_candidate && sh_kmax >= 2) {
-    const bool crowd = c->plan.crowd;
-    const double P = (double)maxP;
-    const double total = (double)n_scenes * samples;
-    const uint32_t paths = 4u + 2u * n_w + 2u * n_v;
-    const uint32_t P2max = (maxP + 1u) / 2u;
-    // thread-per-trajectory: throughput cost of a trajectory-step / one step of a lone warp;
-    // block-per-trajectory: a trajectory-step at full occupancy / one step of one block
-    const double resident = crowd ? (double)c->plan.grid : (double)c->sm_count * c->plan.k * c->plan.T;
-    const double t_ts_ns = crowd ? 0.2 + 0.00085 * P * P : 0.1 + 0.017 * P + 0.0008 * P * P;
-    const double t_lat_us = crowd ? 2.0 + 0.00025 * P * P : 1.3 + 0.25 * P + 0.028 * P * P;
-    const double path_waves = crowd ? std::ceil((double)n_scenes * paths / resident) : 1.0;
-    const double saved_us = total * sh_mean_s0 * t_ts_ns * 1e-3;
-    const double cost_us = (1.0 + path_waves) * sh_kmax * t_lat_us + 30.0;
-    const uint32_t rec = crowd ? (uint32_t)align_up(16u + 32u * P2max + 2u * P2max, 16)
-                               : (uint32_t)align_up(sizeof(SfwCkptHdr) + 32u * P2max, 16);
-    const size_t need = (size_t)n_scenes * paths * (sh_kmax + 1u) * rec;
-    if (total >= 2.5 * resident && saved_us > 2.0 * cost_us && need <= ((size_t)8 << 30)) {
-      if (need > c->share_cap) {
-        CK(c, cudaStreamSynchronize(c->stream));
-        if (c->share_buf)
-          cudaFree(c->share_buf);
-        c->share_buf = nullptr;
-        c->share_cap = 0;
-        CK(c, cudaMalloc((void **)&c->share_buf, need));
-        c->share_cap = need;
-      }
-      B.share.records = c->share_buf;
-      B.share.kv = reinterpret_cast<const uint16_t *>(dv + o_skv);
-      B.share.kw = reinterpret_cast<const uint16_t *>(dv + o_skw);
-      B.share.dirv = dv + o_sdv;
-      B.share.dirw = dv + o_sdw;
-      B.share.col_perm = reinterpret_cast<const uint32_t *>(dv + o_sperm);
-      B.share.row_perm = reinterpret_cast<const uint32_t *>(dv + o_srperm);
-      B.share.sample_perm = sh_sperm.empty() ? nullptr : reinterpret_cast<const uint32_t *>(dv + o_ssperm);
-      B.share.scene_stride = (uint64_t)paths * (sh_kmax + 1u) * rec;
-      B.share.rec_bytes = rec;
-      B.share.kmax = sh_kmax;
-      B.share.mode = 0;
-      c->share_active = true;
-      c->share_paths = paths;
-      c->share_mean_s0 = sh_mean_s0;
+  c->share_warp = 0;
+  if (share_on) {
+    if (share_need > c->share_cap) {
+      CK(c, cudaStreamSynchronize(c->stream));
+      if (c->share_buf)
+        cudaFree(c->share_buf);
+      c->share_buf = nullptr;
+      c->share_cap = 0;
+      CK(c, cudaMalloc((void **)&c->share_buf, share_need));
+      c->share_cap = share_need;
     }
+    B.share.records = c->share_buf;
+    B.share.kv = reinterpret_cast<const uint16_t *>(dv + o_skv);
+    B.share.kw = reinterpret_cast<const uint16_t *>(dv + o_skw);
+    B.share.dirv = dv + o_sdv;
+    B.share.dirw = dv + o_sdw;
+    B.share.col_perm = reinterpret_cast<const uint32_t *>(dv + o_sperm);
+    B.share.row_perm = reinterpret_cast<const uint32_t *>(dv + o_srperm);
+    B.share.lvl_rows = reinterpret_cast<const uint32_t *>(dv + o_slr);
+    B.share.lvl_cols = reinterpret_cast<const uint32_t *>(dv + o_slc);
+    B.share.chunk_map = sh_chunk_map.empty() ? nullptr : reinterpret_cast<const uint32_t *>(dv + o_scm);
+    B.share.scene_stride = (uint64_t)share_paths * (sh_kmax + 1u) * share_rec;
+    B.share.rec_bytes = share_rec;
+    B.share.kmax = sh_kmax;
+    B.share.mode = 0;
+    c->share_active = true;
+    c->share_warp = share_warp;
+    c->share_paths = share_paths;
+    c->share_mean_s0 = sh_mean_s0;
   }
   if (win_wp) {
     rc = make_tensor_map(c, B.maps, map_pitch, map_rows, n_scenes, win_wp, win_h);
@@ -924,7 +1015,7 @@ int sfw_set_prefix_sharing(sfw_ctx *c, int on) {
   if (!c)
     return SFW_ERR_ARG;
   std::lock_guard<std::mutex> lk(c->mu);
-  c->share_allowed = on != 0;
+  c->share_allowed = on < 0 ? 0 : on > 2 ? 2 : on;
   return SFW_OK;
 }
 
@@ -1023,16 +1114,27 @@ int sfw_run(sfw_ctx *c) {
     // (the path launches are latency bound: small blocks, so that every scene's few paths are resident at once)
     SfwBatchDev W = B;
     const uint32_t T1 = 32, T2 = 128;
+    const uint32_t per = SFW_PATH_WARP_THREADS / 32u;
+    const size_t smw = sfw_small_smem_bytes(B.win_wp, B.win_h, c->plan.maxP, c->plan.maxM, c->plan.maxF,
+                                            SFW_PATH_WARP_THREADS);
     W.share.mode = 1;
     W.tiles_per_scene = 1;
-    CK(c, sfw_launch_small(W, c->tmap, T1,
-                           sfw_small_smem_bytes(B.win_wp, B.win_h, c->plan.maxP, c->plan.maxM, c->plan.maxF, T1),
-                           c->stream));
+    if (c->share_warp & 1u) // a warp per path, a lane per pedestrian pair
+      CK(c, sfw_launch_warp_paths(W, c->tmap, smw, c->stream));
+    else
+      CK(c, sfw_launch_small(W, c->tmap, T1,
+                             sfw_small_smem_bytes(B.win_wp, B.win_h, c->plan.maxP, c->plan.maxM, c->plan.maxF, T1),
+                             c->stream));
     W.share.mode = 2;
-    W.tiles_per_scene = (c->share_paths - 4u + T2 - 1u) / T2;
-    CK(c, sfw_launch_small(W, c->tmap, T2,
-                           sfw_small_smem_bytes(B.win_wp, B.win_h, c->plan.maxP, c->plan.maxM, c->plan.maxF, T2),
-                           c->stream));
+    if (c->share_warp & 2u) {
+      W.tiles_per_scene = (c->share_paths - 4u + per - 1u) / per;
+      CK(c, sfw_launch_warp_paths(W, c->tmap, smw, c->stream));
+    } else {
+      W.tiles_per_scene = (c->share_paths - 4u + T2 - 1u) / T2;
+      CK(c, sfw_launch_small(W, c->tmap, T2,
+                             sfw_small_smem_bytes(B.win_wp, B.win_h, c->plan.maxP, c->plan.maxM, c->plan.maxF, T2),
+                             c->stream));
+    }
     W.share.mode = 3;
     W.tiles_per_scene = B.tiles_per_scene;
     CK(c, sfw_launch_small(W, c->tmap, c->plan.T, c->plan.smem, c->stream));
@@ -1205,5 +1307,6 @@ uint64_t sfw_d2h_bytes(const sfw_ctx *c) {
   return (c && c->staged) ? (sizeof(SfwBest) + 4ull * c->out_samples) * c->B.n_scenes : 0;
 }
 const char *sfw_last_kernel(const sfw_ctx *c) { return c ? c->last_kernel : "none"; }
+double sfw_shared_prefix_steps(const sfw_ctx *c) { return (c && c->share_active) ? c->share_mean_s0 : 0.0; }
 
 } // extern "C"

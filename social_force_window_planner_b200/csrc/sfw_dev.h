@@ -21,6 +21,7 @@
 #define SFW_CROWD_THREADS 256  /* block-per-trajectory kernel (sfw_crowd.cu) */
 #define SFW_MAX_PEDS_CROWD 4096
 #define SFW_MAX_BLOCK_SMALL 512 /* launch bound of the thread-per-trajectory kernel (128 regs/thread) */
+#define SFW_PATH_WARP_THREADS 128 /* block of the warp-per-path record writer: 4 paths */
 
 struct SfwSceneDev {
   // robot rollout start (FP64 world frame) — SfwRobot
@@ -84,13 +85,17 @@ struct SfwShareDev {
   uint8_t *records;         // [scene][4 + 2 n_w + 2 n_v paths][kmax + 1 step counts][rec_bytes]
   const uint16_t *kv, *kw;  // [scene][n_v], [scene][n_w]
   const uint8_t *dirv, *dirw; // 1 = ramping up
-  // launch 3 walks the grid in fork-step order: a warp = 32 consecutive columns of col_perm (sorted by kw) on one
-  // row, consecutive warps = consecutive rows of row_perm (sorted by kv) on the same 32 columns -> the lanes of a
-  // warp and the warps of a block start (and finish) together
+  // launch 3 walks the grid in fork-step order (scene 0's tables, any fixed order is correct for the others):
+  // thread position `pos` -> the pos-th sample when all are sorted by max(kv, kw).  No per-sample table: with
+  // rows sorted by kv (row_perm), columns by kw (col_perm) and lvl_rows[k] / lvl_cols[k] = how many rows / columns
+  // fork before step k, the samples that fork before step k are the lvl_rows[k] x lvl_cols[k] corner of the sorted
+  // grid, and level k itself is (rows of level k) x (columns up to level k) followed by (rows before level k) x
+  // (columns of level k).  A warp is therefore 32 samples that fork together whatever the aspect of the grid.
   const uint32_t *col_perm, *row_perm;
-  // grids of at most 65 536 samples: every sample sorted by its fork step (scene 0's tables), so that a warp is
-  // 32 samples that fork together whatever the grid's aspect (nullptr: use the row / column walk above)
-  const uint32_t *sample_perm;
+  const uint32_t *lvl_rows, *lvl_cols; // [kmax + 2]
+  // one-wave launches: chunk_map[idx / 32] = which 32 sorted samples warp idx / 32 takes (deals long and short
+  // warps evenly over blocks and schedulers); nullptr = identity
+  const uint32_t *chunk_map;
   uint64_t scene_stride;
   uint32_t rec_bytes, kmax;
   uint32_t mode, pad0;      // 0 off, 1 / 2 path writers, 3 reader

@@ -50,11 +50,18 @@
 // SHARE: rollout prefix sharing (SfwShareDev): the same kernel simulates the shared paths and writes their
 // per-step records (B.share.mode 1, 2) or starts every sample from the record of its fork point (mode 3).
 // The plain instantiation compiles all of that out.
+// SHARE == 2: the path writer with one WARP per path and one lane per pedestrian pair.  A lone thread walking all
+// pairs of a path is latency bound (23 us per step with 20 pedestrians); here lane k evaluates only the
+// interactions of its own pair -- the reactions from the pairs before it, then its actions on the pairs after it,
+// with the very calls and in the very order the thread-per-trajectory pass uses -- so the records are bit-identical
+// and a step costs what P2 pair evaluations cost, not P2^2 / 2.  Rollout and footprint are computed redundantly by
+// every lane (uniform).  Scenes with pedestrian groups use the thread-per-path writer (SHARE == 1).
 #define SFW_HUGE_TARGET 1.0e300 /* velocity target that keeps step_velocity saturated for ever */
-template <int MAXT, bool SHARE>
+template <int MAXT, int SHARE>
 __global__ void __launch_bounds__(MAXT, 1)
 sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr bool WARP = SHARE == 2;
   const uint32_t T = blockDim.x;
   const uint32_t tid = threadIdx.x;
   const uint32_t scene = blockIdx.x / B.tiles_per_scene;
@@ -199,21 +206,36 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
     const uint8_t *dirv = H.dirv + (size_t)scene * B.n_v, *dirw = H.dirw + (size_t)scene * n_w;
     uint8_t *base = H.records + (size_t)scene * H.scene_stride;
     const size_t R = H.rec_bytes, K1 = (size_t)H.kmax + 1u;
-    const uint32_t p = tile * T + tid; // writer launches: path number
+    const uint32_t p = WARP ? tile * (T >> 5) + (tid >> 5) : tile * T + tid; // writer launches: path number
     if (share_mode == 3u) {
+      // sorted position of this thread (sharing always runs the whole grid: first == 0)
+      uint32_t pos = idx;
+      if (H.chunk_map) {
+        const uint32_t ch = idx >> 5;
+        pos = ch < ((last + 31u) >> 5) ? H.chunk_map[ch] * 32u + (idx & 31u) : last;
+      }
+      in_range = pos < last;
       if (in_range) {
+        // level of pos: the largest k with lvl_rows[k] * lvl_cols[k] <= pos
+        uint32_t lo = 0u, hi = H.kmax + 1u;
+        while (hi - lo > 1u) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (H.lvl_rows[mid] * H.lvl_cols[mid] <= pos)
+            lo = mid;
+          else
+            hi = mid;
+        }
+        const uint32_t r0 = H.lvl_rows[lo], r1 = H.lvl_rows[lo + 1u], c0 = H.lvl_cols[lo], c1 = H.lvl_cols[lo + 1u];
+        const uint32_t local = pos - r0 * c0, n_a = (r1 - r0) * c1;
         uint32_t r, c;
-        if (H.sample_perm) { // samples sorted by fork step
-          const uint32_t sidx = H.sample_perm[idx];
-          r = sidx / n_w;
-          c = sidx - r * n_w;
-        } else if ((n_w & 31u) == 0u) { // warp-major walk: 32 sorted columns x sorted rows
-          const uint32_t w = idx >> 5, chunk = w / B.n_v;
-          r = H.row_perm[w - chunk * B.n_v];
-          c = H.col_perm[chunk * 32u + (idx & 31u)];
-        } else {
-          r = idx / n_w;
-          c = H.col_perm[idx - r * n_w];
+        if (local < n_a) { // rows of this level x columns up to this level
+          const uint32_t q = local / c1;
+          r = H.row_perm[r0 + q];
+          c = H.col_perm[local - q * c1];
+        } else { // earlier rows x columns of this level
+          const uint32_t l2 = local - n_a, nc = c1 - c0, q = l2 / nc;
+          r = H.row_perm[q];
+          c = H.col_perm[c0 + (l2 - q * nc)];
         }
         idx = r * n_w + c;
         v_s = B.linvels[r];
@@ -268,7 +290,9 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   bool alive = in_range && !skipped;
 
   // ---- per-thread state: one shared-memory column per thread (conflict-free LDS.128) ------------
-  float4 *pos = s_pos + tid, *vel = s_vel + tid, *frc = s_frc + tid; // [k * T]
+  // (one column per warp in the warp-per-path writer: every lane stores the same values)
+  const uint32_t col = WARP ? (tid & ~31u) : tid;
+  float4 *pos = s_pos + col, *vel = s_vel + col, *frc = s_frc + col; // [k * T]
   for (uint32_t k = 0; k < P2; ++k) {
     pos[k * T] = s_pos0[k];
     vel[k * T] = s_vel0[k];
@@ -357,6 +381,126 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
         bool hit = false;
         const f2 RX = bc2(prx), RY = bc2(pry), RVX = bc2(rvxf), RVY = bc2(rvyf);
         const f2 DT = bc2(dtf);
+        if constexpr (WARP) {
+          const uint32_t k = tid & 31u; // my pedestrian pair
+          const bool mine = k < P2;
+          const float4 pa = mine ? pos[k * T] : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 va = mine ? vel[k * T] : make_float4(0.f, 0.f, 0.f, 0.f);
+          const f2 AX = mk2(pa.x, pa.y), AY = mk2(pa.z, pa.w);
+          const f2 AVX = mk2(va.x, va.y), AVY = mk2(va.z, va.w);
+          f2 fx = bc2(0.f), fy = bc2(0.f), fm = bc2(0.f);
+          f2 FX = bc2(0.f), FY = bc2(0.f);                                        // reactions from earlier pairs
+          f2 s0x = bc2(0.f), s0y = bc2(0.f), s1x = bc2(0.f), s1y = bc2(0.f);      // actions on later pairs
+          for (uint32_t j = 0; j < P2; ++j) {
+            const float4 pb = pos[j * T], vb = vel[j * T]; // broadcast
+            if (mine && j != k) {
+              const bool act = j > k; // pair k acts on pair j, or receives the reaction of pair j's action on it
+              const float4 pA = act ? pa : pb, vA = act ? va : vb, pB = act ? pb : pa, vB = act ? vb : va;
+              const f2 BX = mk2(pB.x, pB.y), BY = mk2(pB.z, pB.w);
+              const f2 BVX = mk2(vB.x, vB.y), BVY = mk2(vB.z, vB.w);
+              f2 hx, hy, gx2, gy2, hm;
+              pair_force2<false>(K, bc2(pA.x), bc2(pA.z), bc2(vA.x), bc2(vA.z), BX, BY, BVX, BVY, hx, hy, hm);
+              pair_force2<false>(K, bc2(pA.y), bc2(pA.w), bc2(vA.y), bc2(vA.w), BX, BY, BVX, BVY, gx2, gy2, hm);
+              if (act) {
+                s0x = add2(s0x, hx);
+                s0y = add2(s0y, hy);
+                s1x = add2(s1x, gx2);
+                s1y = add2(s1y, gy2);
+              } else {
+                FX = sub2(FX, add2(hx, gx2));
+                FY = sub2(FY, add2(hy, gy2));
+              }
+            }
+          }
+          float npx0 = 0.f, npx1 = 0.f, npy0 = 0.f, npy1 = 0.f, nvx0 = 0.f, nvx1 = 0.f, nvy0 = 0.f, nvy1 = 0.f;
+          uint32_t clr_lo = 0u, clr_hi = 0u;
+          bool myhit = false;
+          if (mine) {
+            pair_force2<true>(K, AX, AY, AVX, AVY, RX, RY, RVX, RVY, fx, fy, fm);
+            FX = add2(FX, fx);
+            FY = add2(FY, fy);
+            {
+              float gx_, gy_, gm_;
+              pair_force<false>(K, pa.x, pa.z, va.x, va.z, pa.y, pa.w, va.y, va.w, gx_, gy_, gm_);
+              FX = add2(FX, mk2(gx_, -gx_));
+              FY = add2(FY, mk2(gy_, -gy_));
+            }
+            {
+              float l0, h0, l1, h1;
+              un2(s0x, l0, h0);
+              un2(s1x, l1, h1);
+              FX = add2(FX, mk2(l0 + h0, l1 + h1));
+              un2(s0y, l0, h0);
+              un2(s1y, l1, h1);
+              FY = add2(FY, mk2(l0 + h0, l1 + h1));
+            }
+            f2 ox, oy;
+            obstacle_sum2(s_obs, (int)M, B.c_obs, AX, AY, ox, oy);
+            const float4 G = s_goal[k], Pp = s_par[k], Pc = s_par2[k];
+            const f2 gdx = sub2(mk2(G.x, G.y), AX), gdy = sub2(mk2(G.z, G.w), AY);
+            float g20, g21;
+            un2(fma2(gdx, gdx, mul2(gdy, gdy)), g20, g21);
+            const bool hg0 = (goalmask >> (2u * k)) & 1ull, hg1 = (goalmask >> (2u * k + 1u)) & 1ull;
+            const bool go0 = hg0 && g20 > Pp.x, go1 = hg1 && g21 > Pp.y;
+            const f2 gs = mk2(go0 ? rsqrt_approx(g20) * Pp.z : 0.f, go1 ? rsqrt_approx(g21) * Pp.w : 0.f);
+            const f2 c1 = mk2(go0 ? B.kd_tau : B.inv_tau, go1 ? B.kd_tau : B.inv_tau);
+            const f2 dfx = mul2(c1, sub2(mul2(gdx, gs), AVX));
+            const f2 dfy = mul2(c1, sub2(mul2(gdy, gs), AVY));
+            const f2 OS = mk2(Pc.x, Pc.y);
+            const f2 Fx = add2(add2(dfx, FX), mul2(OS, ox));
+            const f2 Fy = add2(add2(dfy, FY), mul2(OS, oy));
+            f2 nvx = fma2(Fx, DT, AVX), nvy = fma2(Fy, DT, AVY);
+            float v20, v21;
+            un2(fma2(nvx, nvx, mul2(nvy, nvy)), v20, v21);
+            const f2 sc = mk2(v20 > Pc.z ? Pp.z * rsqrt_approx(v20) : 1.0f, v21 > Pc.w ? Pp.w * rsqrt_approx(v21) : 1.0f);
+            nvx = mul2(nvx, sc);
+            nvy = mul2(nvy, sc);
+            const f2 npx = fma2(nvx, DT, AX), npy = fma2(nvy, DT, AY);
+            un2(npx, npx0, npx1);
+            un2(npy, npy0, npy1);
+            un2(nvx, nvx0, nvx1);
+            un2(nvy, nvy0, nvy1);
+            {
+              const f2 hx = sub2(mk2(G.x, G.y), npx), hy = sub2(mk2(G.z, G.w), npy);
+              float h0, h1;
+              un2(fma2(hx, hx, mul2(hy, hy)), h0, h1);
+              uint64_t clr = 0ull;
+              if (hg0 && h0 <= Pp.x)
+                clr |= 1ull << (2u * k);
+              if (hg1 && h1 <= Pp.y)
+                clr |= 1ull << (2u * k + 1u);
+              clr_lo = (uint32_t)clr;
+              clr_hi = (uint32_t)(clr >> 32);
+            }
+            {
+              const f2 cx = sub2(bc2(nrx), npx), cy = sub2(bc2(nry), npy);
+              float c0, c1_;
+              un2(fma2(cx, cx, mul2(cy, cy)), c0, c1_);
+              myhit = (c0 <= rr2) | (c1_ <= rr2);
+            }
+          }
+          __syncwarp(); // every lane has read the old state
+          if (mine) {
+            pos[k * T] = make_float4(npx0, npx1, npy0, npy1);
+            vel[k * T] = make_float4(nvx0, nvx1, nvy0, nvy1);
+          }
+          // ordered sums over the pairs, as the one-thread pass accumulates them
+          {
+            float fxl, fxh, fyl, fyh, fml, fmh;
+            un2(fx, fxl, fxh);
+            un2(fy, fyl, fyh);
+            un2(fm, fml, fmh);
+            for (uint32_t q = 0; q < P2; ++q) {
+              rfx2 = sub2(rfx2, mk2(__shfl_sync(0xffffffffu, fxl, q), __shfl_sync(0xffffffffu, fxh, q)));
+              rfy2 = sub2(rfy2, mk2(__shfl_sync(0xffffffffu, fyl, q), __shfl_sync(0xffffffffu, fyh, q)));
+              wp2 = add2(wp2, mk2(__shfl_sync(0xffffffffu, fml, q), __shfl_sync(0xffffffffu, fmh, q)));
+            }
+          }
+          hit = __any_sync(0xffffffffu, myhit);
+          goalmask &= ~((uint64_t)__reduce_or_sync(0xffffffffu, clr_lo) |
+                        ((uint64_t)__reduce_or_sync(0xffffffffu, clr_hi) << 32));
+          __syncwarp(); // new state visible to the warp
+        } else {
         // group forces of computeForces (lightsfm computeGroupForce): added to the (zeroed) accumulators
         if (n_groups) {
           const uint32_t *gt = B.groups + scp->grp_off;
@@ -480,6 +624,7 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
             hit |= (c0 <= rr2) | (c1_ <= rr2);
           }
         }
+        } // !WARP
         float rfx, rfy, wp;
         {
           float l, h;
@@ -528,7 +673,7 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
         h->alive = alive ? 1 : 0;
         if (alive) {
           float4 *pv = reinterpret_cast<float4 *>(rec + sizeof(SfwCkptHdr));
-          for (uint32_t k = 0; k < P2; ++k) {
+          for (uint32_t k = WARP ? (tid & 31u) : 0u; k < P2; k += WARP ? 32u : 1u) {
             pv[2u * k] = pos[k * T];
             pv[2u * k + 1u] = vel[k * T];
           }
@@ -816,6 +961,7 @@ const SmallVariant kSmallShare[] = {
     {448, sfw_score_small<448, true>, "sfw_score_small<448,share>"},
     {512, sfw_score_small<512, true>, "sfw_score_small<512,share>"},
 };
+const SmallVariant kWarpPath = {SFW_PATH_WARP_THREADS, sfw_score_small<SFW_PATH_WARP_THREADS, 2>, "sfw_score_small<warp-per-path>"};
 const SmallVariant &small_variant(uint32_t T, bool share = false) {
   const SmallVariant *tab = share ? kSmallShare : kSmall;
   for (int i = 0; i < 3; ++i)
@@ -848,12 +994,22 @@ cudaError_t sfw_small_max_dynamic_smem(size_t *bytes) {
           return e;
         dyn = std::min(dyn, (size_t)optin - fa.sharedSizeBytes);
       }
+    {
+      cudaFuncAttributes fa;
+      e = cudaFuncGetAttributes(&fa, kWarpPath.fn);
+      if (e != cudaSuccess)
+        return e;
+      dyn = std::min(dyn, (size_t)optin - fa.sharedSizeBytes);
+    }
     for (const SmallVariant *tab : {kSmall, kSmallShare})
       for (int i = 0; i < 3; ++i) {
         e = cudaFuncSetAttribute(tab[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (e != cudaSuccess)
           return e;
       }
+    e = cudaFuncSetAttribute(kWarpPath.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess)
+      return e;
     cached = dyn;
   }
   *bytes = cached;
@@ -864,6 +1020,15 @@ cudaError_t sfw_launch_small(const SfwBatchDev &B, const CUtensorMap &tmap, uint
                              size_t smem_bytes, cudaStream_t stream) {
   const uint32_t grid = B.n_scenes * B.tiles_per_scene;
   small_variant(T, B.share.mode != 0).fn<<<grid, T, smem_bytes, stream>>>(B, tmap);
+  return cudaGetLastError();
+}
+
+// Path writer with one warp per path (B.share.mode 1 or 2; B.tiles_per_scene = blocks of SFW_PATH_WARP_THREADS / 32
+// paths per scene).
+cudaError_t sfw_launch_warp_paths(const SfwBatchDev &B, const CUtensorMap &tmap, size_t smem_bytes,
+                                  cudaStream_t stream) {
+  const uint32_t grid = B.n_scenes * B.tiles_per_scene;
+  kWarpPath.fn<<<grid, SFW_PATH_WARP_THREADS, smem_bytes, stream>>>(B, tmap);
   return cudaGetLastError();
 }
 

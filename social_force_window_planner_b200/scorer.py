@@ -70,9 +70,10 @@ class Scorer:
         """Kernel selection policy (``sfw_set_policy``): AUTO switches small grids to the low-latency kernel."""
         self._check(self._lib.sfw_set_policy(self._ctx, policy))
 
-    def set_prefix_sharing(self, on: bool):
-        """Rollout prefix sharing on dense multi-wave grids (``sfw_set_prefix_sharing``); bit-identical results."""
-        self._check(self._lib.sfw_set_prefix_sharing(self._ctx, 1 if on else 0))
+    def set_prefix_sharing(self, on):
+        """Rollout prefix sharing (``sfw_set_prefix_sharing``); bit-identical results.  False / 0 = never,
+        True / 1 = when the library's cost model says it pays, 2 = whenever the batch allows it."""
+        self._check(self._lib.sfw_set_prefix_sharing(self._ctx, int(on)))
 
     def set_row_slab(self, row_begin: int, row_end: int):
         self._check(self._lib.sfw_set_row_slab(self._ctx, row_begin, row_end))
@@ -215,3 +216,8 @@ class Scorer:
     @property
     def last_kernel(self) -> str:
         return self._lib.sfw_last_kernel(self._ctx).decode()
+
+    @property
+    def shared_prefix_steps(self) -> float:
+        """Mean number of leading steps a sample of the staged batch takes from a shared path (0: sharing off)."""
+        return float(self._lib.sfw_shared_prefix_steps(self._ctx))

@@ -420,11 +420,12 @@ def test_long_horizon_without_staged_window(scorer, policy):
 
 
 # ---- rollout prefix sharing -------------------------------------------------------------------------------
-@pytest.mark.parametrize("name,n_scenes", [("C4", 1), ("C3", 64)])
+@pytest.mark.parametrize("name,n_scenes", [("C4", 1), ("C3", 64), ("C1", 1), ("C1", 3)])
 def test_prefix_sharing_is_bit_identical(name, n_scenes):
-    """Dense multi-wave grids start every sample from the shared state of its fork point (SfwShareDev): same
-    arithmetic in the same order, so the cost vector, the recorded-point counts and the winners must equal the
-    unshared run bit for bit — and the shared run must actually have been taken."""
+    """Dense grids start every sample from the shared state of its fork point (SfwShareDev): same arithmetic in
+    the same order, so the cost vector, the recorded-point counts and the winners must equal the unshared run bit
+    for bit — and the shared run must actually have been taken.  C1 x 1 is the one-wave flavour: chunks of
+    fork-sorted samples dealt over blocks and schedulers, path records written by the warp-per-path kernel."""
     from social_force_window_planner_b200.scorer import Scorer
     wl = S.WORKLOADS[name]
     scs = S.make_scenes(wl, n_scenes)
@@ -453,6 +454,43 @@ def test_prefix_sharing_is_bit_identical(name, n_scenes):
     assert np.array_equal(best_on, best_off)
     assert pts_on == pts_off
     print(name, k_on, "valid", float((costs_on >= 0).mean()))
+
+
+@pytest.mark.parametrize("n_v,n_w,n_scenes,n_peds,groups", [(100, 77, 1, 20, False), (37, 41, 5, 7, False),
+                                                           (64, 96, 2, 12, True), (33, 1000, 1, 3, False)])
+def test_prefix_sharing_forced_on_ragged_grids(n_v, n_w, n_scenes, n_peds, groups):
+    """Sharing forced (mode 2) through the thread-per-trajectory kernel on shapes the cost model would not pick:
+    sample counts that are no multiple of 32 (a partial last chunk), several scenes in one wave, odd pedestrian
+    counts (a dummy pair half), pedestrian groups (thread-per-path writers instead of warp-per-path)."""
+    from social_force_window_planner_b200.scorer import Scorer
+    wl = dataclasses.replace(S.WORKLOADS["C1"], n_v=n_v, n_w=n_w, n_peds=n_peds)
+    scs = S.make_scenes(wl, n_scenes)
+    for k, sc in enumerate(scs):
+        r = list(sc.robot)
+        r[3] = float(np.float32(0.1 + 0.1 * k))
+        r[5] = float(np.float32(-0.3 + 0.2 * k))
+        r[10] = r[3]
+        sc.robot = tuple(r)
+        if groups:
+            sc.peds["group_id"][:9] = np.arange(9) // 3
+    p = wl.params()
+    lin, ang = wl.sample_arrays()
+    s2 = Scorer(0)
+    try:
+        s2.set_policy(Scorer.POLICY_THROUGHPUT)
+        s2.set_prefix_sharing(2)
+        costs_on, best_on = s2.score(p, scs, lin, ang)
+        k_on = s2.last_kernel
+        s2.set_prefix_sharing(0)
+        costs_off, best_off = s2.score(p, scs, lin, ang)
+        k_off = s2.last_kernel
+    finally:
+        s2.close()
+    assert "share" in k_on and "share" not in k_off, (k_on, k_off)
+    assert np.array_equal(costs_on, costs_off)
+    assert np.array_equal(best_on, best_off)
+    assert (costs_on >= 0).any()
+    _spot_check(p, scs[-1], lin, ang, costs_on[-1], [0, n_w + 1, n_v * n_w - 1])
 
 
 def test_prefix_sharing_crowd_kernel_is_bit_identical():
