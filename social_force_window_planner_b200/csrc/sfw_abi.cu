@@ -959,6 +959,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
       c->share_buf = nullptr;
       c->share_cap = 0;
       CK(c, cudaMalloc((void **)&c->share_buf, share_need));
+      CK(c, cudaMemsetAsync(c->share_buf, 0, share_need, c->stream)); // record flags (SfwCkptHdr::epoch) start clear
       c->share_cap = share_need;
     }
     B.share.records = c->share_buf;
@@ -1117,6 +1118,16 @@ int sfw_run(sfw_ctx *c) {
     const uint32_t per = SFW_PATH_WARP_THREADS / 32u;
     const size_t smw = sfw_small_smem_bytes(B.win_wp, B.win_h, c->plan.maxP, c->plan.maxM, c->plan.maxF,
                                             SFW_PATH_WARP_THREADS);
+    if (c->share_warp == 3u) {
+      // both path stages in one launch: tile 0 of a scene writes the 4 doubly saturated paths, the other tiles
+      // wait (per record) for the one they continue from
+      W.share.mode = 4;
+      c->share_epoch = c->share_epoch == 0xffffffffu ? 1u : c->share_epoch + 1u;
+      W.share.epoch = c->share_epoch;
+      W.tiles_per_scene = 1u + (c->share_paths - 4u + per - 1u) / per;
+      CK(c, sfw_launch_warp_paths(W, c->tmap, smw, c->stream));
+      c->launches -= 1; // (3 is added below)
+    } else {
     W.share.mode = 1;
     W.tiles_per_scene = 1;
     if (c->share_warp & 1u) // a warp per path, a lane per pedestrian pair
@@ -1134,6 +1145,7 @@ int sfw_run(sfw_ctx *c) {
       CK(c, sfw_launch_small(W, c->tmap, T2,
                              sfw_small_smem_bytes(B.win_wp, B.win_h, c->plan.maxP, c->plan.maxM, c->plan.maxF, T2),
                              c->stream));
+    }
     }
     W.share.mode = 3;
     W.tiles_per_scene = B.tiles_per_scene;

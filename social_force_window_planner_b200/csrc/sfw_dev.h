@@ -79,7 +79,8 @@ struct SfwCkptHdr {
   float prx, pry, rvxf, rvyf;
   uint64_t goalmask;
   int32_t npts, alive;
-  uint64_t pad;
+  uint32_t epoch; // merged path launch (mode 4): the record is complete for run `epoch` (release / acquire)
+  uint32_t pad;
 };
 struct SfwShareDev {
   uint8_t *records;         // [scene][4 + 2 n_w + 2 n_v paths][kmax + 1 step counts][rec_bytes]
@@ -98,7 +99,9 @@ struct SfwShareDev {
   const uint32_t *chunk_map;
   uint64_t scene_stride;
   uint32_t rec_bytes, kmax;
-  uint32_t mode, pad0;      // 0 off, 1 / 2 path writers, 3 reader
+  uint32_t mode, epoch;     // 0 off, 1 / 2 path writers, 3 reader, 4 both path stages in one launch of the
+                            // warp-per-path writer (tile 0 of a scene = the 4 doubly saturated paths; the others
+                            // wait for the record they continue from: flag = SfwCkptHdr::epoch == epoch)
 };
 
 struct SfwBatchDev {

@@ -198,7 +198,13 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   int s0 = 0;                           // first step this thread simulates itself
   const uint8_t *ck_in = nullptr;       // record it starts from (nullptr: the scene's initial state)
   uint8_t *ck_out = nullptr;            // writer launches: this path's records [step count]
-  const uint32_t share_mode = SHARE ? B.share.mode : 0u;
+  uint32_t share_mode = SHARE ? B.share.mode : 0u;
+  uint32_t ptile = tile;
+  const bool merged = WARP && share_mode == 4u; // both path stages in this launch
+  if (merged) {
+    share_mode = tile == 0u ? 1u : 2u;
+    ptile = tile ? tile - 1u : 0u;
+  }
   const bool writer = SHARE && (share_mode == 1u || share_mode == 2u);
   if (SHARE && share_mode) {
     const SfwShareDev &H = B.share;
@@ -206,7 +212,7 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
     const uint8_t *dirv = H.dirv + (size_t)scene * B.n_v, *dirw = H.dirw + (size_t)scene * n_w;
     uint8_t *base = H.records + (size_t)scene * H.scene_stride;
     const size_t R = H.rec_bytes, K1 = (size_t)H.kmax + 1u;
-    const uint32_t p = WARP ? tile * (T >> 5) + (tid >> 5) : tile * T + tid; // writer launches: path number
+    const uint32_t p = WARP ? ptile * (T >> 5) + (tid >> 5) : tile * T + tid; // writer launches: path number
     if (share_mode == 3u) {
       // sorted position of this thread (sharing always runs the whole grid: first == 0)
       uint32_t pos = idx;
@@ -293,10 +299,11 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   // (one column per warp in the warp-per-path writer: every lane stores the same values)
   const uint32_t col = WARP ? (tid & ~31u) : tid;
   float4 *pos = s_pos + col, *vel = s_vel + col, *frc = s_frc + col; // [k * T]
-  for (uint32_t k = 0; k < P2; ++k) {
+  for (uint32_t k = WARP ? (tid & 31u) : 0u; k < P2; k += WARP ? 32u : 1u) { // warp writer: lane k owns pair k
     pos[k * T] = s_pos0[k];
     vel[k * T] = s_vel0[k];
-    frc[k * T] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!WARP)
+      frc[k * T] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   uint64_t goalmask = scp->goal_mask;
 
@@ -314,28 +321,44 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   double social_work = 0.0, costmap_sum = 0.0;
   int npts = 0;
   const int S = B.num_steps;
-  if (SHARE && ck_in) { // start from the shared path's record of this thread's fork point
-    const SfwCkptHdr *h = reinterpret_cast<const SfwCkptHdr *>(ck_in);
-    x = h->x;
-    y = h->y;
-    th = h->th;
-    vx = h->vx;
-    vth = h->vth;
-    social_work = h->social_work;
-    costmap_sum = h->costmap_sum;
-    prx = h->prx;
-    pry = h->pry;
-    rvxf = h->rvxf;
-    rvyf = h->rvyf;
-    goalmask = h->goalmask;
-    npts = h->npts;
-    alive = alive && h->alive != 0;
-    const float4 *pv = reinterpret_cast<const float4 *>(ck_in + sizeof(SfwCkptHdr));
-    for (uint32_t k = 0; k < P2; ++k) {
-      pos[k * T] = pv[2u * k];
-      vel[k * T] = pv[2u * k + 1u];
+  if (WARP && merged && ck_in) {
+    // the record this path continues from is written by tile 0 of the scene in this very launch (a lower block
+    // index, hence already dispatched): wait for its flag
+    const uint32_t *flag = &reinterpret_cast<const SfwCkptHdr *>(ck_in)->epoch;
+    uint32_t seen;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+      if (seen == B.share.epoch)
+        break;
+      __nanosleep(256);
     }
   }
+  if (SHARE && ck_in) { // start from the shared path's record of this thread's fork point
+    // (the warp-per-path writer may be reading what another block wrote moments ago: L2 loads only)
+    const SfwCkptHdr *h = reinterpret_cast<const SfwCkptHdr *>(ck_in);
+    auto ld = [](const auto *q) { return WARP ? __ldcg(q) : *q; };
+    x = ld(&h->x);
+    y = ld(&h->y);
+    th = ld(&h->th);
+    vx = ld(&h->vx);
+    vth = ld(&h->vth);
+    social_work = ld(&h->social_work);
+    costmap_sum = ld(&h->costmap_sum);
+    prx = ld(&h->prx);
+    pry = ld(&h->pry);
+    rvxf = ld(&h->rvxf);
+    rvyf = ld(&h->rvyf);
+    goalmask = ld(reinterpret_cast<const unsigned long long *>(&h->goalmask));
+    npts = ld(&h->npts);
+    alive = alive && ld(&h->alive) != 0;
+    const float4 *pv = reinterpret_cast<const float4 *>(ck_in + sizeof(SfwCkptHdr));
+    for (uint32_t k = WARP ? (tid & 31u) : 0u; k < P2; k += WARP ? 32u : 1u) {
+      pos[k * T] = ld(&pv[2u * k]);
+      vel[k * T] = ld(&pv[2u * k + 1u]);
+    }
+  }
+  if (WARP)
+    __syncwarp(); // the column is shared by the warp
   const int S_end = writer ? (int)B.share.kmax : S;
   const int i_first = SHARE ? __reduce_min_sync(0xffffffffu, in_range ? s0 : S_end) : 0;
 
@@ -677,6 +700,12 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
             pv[2u * k] = pos[k * T];
             pv[2u * k + 1u] = vel[k * T];
           }
+        }
+        if (WARP && merged && share_mode == 1u) { // publish: every lane's stores, then the flag
+          __threadfence();
+          __syncwarp();
+          if ((tid & 31u) == 0u)
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&h->epoch), "r"(B.share.epoch) : "memory");
         }
       }
     }
