@@ -202,7 +202,7 @@ int sfw_set_policy(sfw_ctx *ctx, int policy);
 
 /* Rollout prefix sharing (on by default; applies from the next sfw_upload).  With acceleration limits, samples
  * whose velocity is still ramping at the full +-a*dt per step are identical for their first steps; on dense
- * multi-wave grids the library simulates those shared prefixes once and starts every sample from the state of
+ * grids (one wave or many) the library simulates those shared prefixes once and starts every sample from the state of
  * its fork point.  The cost vector is bit-identical either way (same arithmetic, same order).
  * on: 0 = never, 1 = when the library's cost model says it pays (default), 2 = whenever the staged batch allows
  * it (grids of >= 1024 samples, >= 8 steps, some saturated ramp; for tests and experiments). */

@@ -571,7 +571,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   }
   // ---- worth it?  Sharing removes the first max(kv, kw) steps of every sample and costs two latency-bound
   // path launches of kmax steps each.  Cost model from scripts/share_probe.py / latency_probe.py (us).
-  bool share_on = false, share_dealt = false;
+  bool share_on = false, share_dealt = false, share_merged = false;
   uint32_t share_warp = 0; // bit 0 / 1: launch 1 / 2 uses the warp-per-path writer
   uint32_t share_rec = 0;
   size_t share_need = 0;
@@ -631,6 +631,14 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
         }
       }
       cost_us = c1 + c2 + 10.0;
+      if (share_warp == 3u) {
+        // both stages in one launch (the second waits for the first's records): only when every block is resident
+        // at once, so that no assumption about the dispatch order is needed
+        int occ = 0;
+        CK(c, sfw_warp_paths_occupancy(smw, &occ));
+        const double blocks = (double)n_scenes * (1.0 + std::ceil(paths2 / (SFW_PATH_WARP_THREADS / 32.0)));
+        share_merged = blocks <= (double)c->sm_count * occ;
+      }
     }
     share_rec = crowd ? (uint32_t)align_up(16u + 32u * P2max + 2u * P2max, 16)
                       : (uint32_t)align_up(sizeof(SfwCkptHdr) + 32u * P2max, 16);
@@ -643,7 +651,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
               "saved %.0f us vs cost %.0f us (%s writers) -> %s\n",
               crowd ? "block-per-trajectory" : "thread-per-trajectory", n_scenes, samples, maxP, num_steps, sh_kmax,
               mean_s0, single ? "one wave" : "several waves", saved_us, cost_us,
-              share_warp == 3u ? "warp" : share_warp == 1u ? "warp + thread" : share_warp == 2u ? "thread + warp" : "thread",
+              share_warp == 3u ? (share_merged ? "warp, one launch" : "warp") : share_warp == 1u ? "warp + thread" : share_warp == 2u ? "thread + warp" : "thread",
               share_on ? "on" : "off");
     if (share_dealt) {
       // One wave: a block-sorted order would leave the blocks of unshortened samples as long as before.  Deal
@@ -978,6 +986,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     B.share.mode = 0;
     c->share_active = true;
     c->share_warp = share_warp;
+    c->share_merged = share_merged;
     c->share_paths = share_paths;
     c->share_mean_s0 = sh_mean_s0;
   }
@@ -1118,7 +1127,7 @@ int sfw_run(sfw_ctx *c) {
     const uint32_t per = SFW_PATH_WARP_THREADS / 32u;
     const size_t smw = sfw_small_smem_bytes(B.win_wp, B.win_h, c->plan.maxP, c->plan.maxM, c->plan.maxF,
                                             SFW_PATH_WARP_THREADS);
-    if (c->share_warp == 3u) {
+    if (c->share_warp == 3u && c->share_merged) {
       // both path stages in one launch: tile 0 of a scene writes the 4 doubly saturated paths, the other tiles
       // wait (per record) for the one they continue from
       W.share.mode = 4;

@@ -49,6 +49,7 @@ struct sfw_ctx {
   int share_allowed = 1;      // sfw_set_prefix_sharing: 0 never, 1 when the cost model says it pays, 2 whenever possible
   bool share_active = false; // decided per upload
   uint32_t share_warp = 0;   // bit 0 / 1: path launch 1 / 2 uses the warp-per-path writer
+  bool share_merged = false; // both path stages in one launch (all blocks co-resident)
   uint32_t share_epoch = 0;  // run counter of the merged path launch (record flags)
   uint8_t *share_buf = nullptr;
   size_t share_cap = 0;

@@ -326,11 +326,14 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
     // index, hence already dispatched): wait for its flag
     const uint32_t *flag = &reinterpret_cast<const SfwCkptHdr *>(ck_in)->epoch;
     uint32_t seen;
+    const long long t0 = clock64();
     for (;;) {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
       if (seen == B.share.epoch)
         break;
       __nanosleep(256);
+      if (clock64() - t0 > (1ll << 33)) // seconds: the host only merges launches whose blocks are all co-resident
+        __trap();
     }
   }
   if (SHARE && ck_in) { // start from the shared path's record of this thread's fork point
@@ -1059,6 +1062,10 @@ cudaError_t sfw_launch_warp_paths(const SfwBatchDev &B, const CUtensorMap &tmap,
   const uint32_t grid = B.n_scenes * B.tiles_per_scene;
   kWarpPath.fn<<<grid, SFW_PATH_WARP_THREADS, smem_bytes, stream>>>(B, tmap);
   return cudaGetLastError();
+}
+
+cudaError_t sfw_warp_paths_occupancy(size_t smem_bytes, int *blocks_per_sm) {
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kWarpPath.fn, SFW_PATH_WARP_THREADS, smem_bytes);
 }
 
 cudaError_t sfw_small_occupancy(uint32_t T, size_t smem_bytes, int *blocks_per_sm) {

@@ -11,6 +11,7 @@ size_t sfw_small_smem_bytes(uint32_t win_wp, uint32_t win_h, uint32_t P, uint32_
 cudaError_t sfw_small_max_dynamic_smem(size_t *bytes);
 const char *sfw_small_kernel_name(uint32_t T, bool share = false); // variant a block of T threads dispatches to
 cudaError_t sfw_small_occupancy(uint32_t T, size_t smem_bytes, int *blocks_per_sm);
+cudaError_t sfw_warp_paths_occupancy(size_t smem_bytes, int *blocks_per_sm);
 cudaError_t sfw_launch_warp_paths(const SfwBatchDev &B, const CUtensorMap &tmap, size_t smem_bytes,
                                   cudaStream_t stream);
 cudaError_t sfw_launch_small(const SfwBatchDev &B, const CUtensorMap &tmap, uint32_t T,
