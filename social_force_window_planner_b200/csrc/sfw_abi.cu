@@ -539,35 +539,36 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
       sh_kmax = std::max<uint32_t>(sh_kmax, k);
     for (uint16_t k : sh_kw)
       sh_kmax = std::max<uint32_t>(sh_kmax, k);
-    // lanes of a warp walk columns in the order of their fork step (scene 0's), so that they start together
-    sh_perm.resize(n_w);
-    for (uint32_t q = 0; q < n_w; ++q)
-      sh_perm[q] = q;
-    std::stable_sort(sh_perm.begin(), sh_perm.end(), [&](uint32_t a, uint32_t b) { return sh_kw[a] < sh_kw[b]; });
-    sh_rperm.resize(n_v);
-    for (uint32_t r = 0; r < n_v; ++r)
-      sh_rperm[r] = r;
-    std::stable_sort(sh_rperm.begin(), sh_rperm.end(), [&](uint32_t a, uint32_t b) { return sh_kv[a] < sh_kv[b]; });
-    // every sample's own fork step (scene 0's tables)
-    {
-      std::vector<double> hv(sh_kmax + 1u, 0.0), hw(sh_kmax + 1u, 0.0);
+    // per scene: rows sorted by kv, columns by kw (counting sorts), how many fork before each step, and the mean
+    // fork step max(kv, kw) over the grid (from the prefix counts)
+    const uint32_t L = sh_kmax + 2u;
+    sh_perm.resize((size_t)n_scenes * n_w);
+    sh_rperm.resize((size_t)n_scenes * n_v);
+    sh_lvl_rows.assign((size_t)n_scenes * L, 0u);
+    sh_lvl_cols.assign((size_t)n_scenes * L, 0u);
+    std::vector<uint32_t> cur(L);
+    double tot = 0.0;
+    for (uint32_t s = 0; s < n_scenes; ++s) {
+      const uint16_t *kvs = sh_kv.data() + (size_t)s * n_v, *kws = sh_kw.data() + (size_t)s * n_w;
+      uint32_t *lr = sh_lvl_rows.data() + (size_t)s * L, *lc = sh_lvl_cols.data() + (size_t)s * L;
       for (uint32_t r = 0; r < n_v; ++r)
-        hv[sh_kv[r]] += 1.0;
+        ++lr[kvs[r] + 1u];
       for (uint32_t q = 0; q < n_w; ++q)
-        hw[sh_kw[q]] += 1.0;
-      double tot = 0.0;
-      for (uint32_t a = 0; a <= sh_kmax; ++a)
-        for (uint32_t b = 0; b <= sh_kmax; ++b)
-          tot += hv[a] * hw[b] * (double)std::max(a, b);
-      sh_mean_s0 = tot / ((double)n_v * n_w);
-      // rows / columns that fork before step k (scene 0)
-      sh_lvl_rows.assign(sh_kmax + 2u, 0u);
-      sh_lvl_cols.assign(sh_kmax + 2u, 0u);
-      for (uint32_t k = 0; k <= sh_kmax; ++k) {
-        sh_lvl_rows[k + 1u] = sh_lvl_rows[k] + (uint32_t)hv[k];
-        sh_lvl_cols[k + 1u] = sh_lvl_cols[k] + (uint32_t)hw[k];
+        ++lc[kws[q] + 1u];
+      for (uint32_t k = 1; k < L; ++k) {
+        lr[k] += lr[k - 1u];
+        lc[k] += lc[k - 1u];
       }
+      for (uint32_t k = 1; k <= sh_kmax; ++k) // sum of max(kv, kw) = sum over k >= 1 of #{max >= k}
+        tot += (double)n_v * n_w - (double)lr[k] * (double)lc[k];
+      std::copy(lr, lr + L, cur.begin());
+      for (uint32_t r = 0; r < n_v; ++r)
+        sh_rperm[(size_t)s * n_v + cur[kvs[r]]++] = r;
+      std::copy(lc, lc + L, cur.begin());
+      for (uint32_t q = 0; q < n_w; ++q)
+        sh_perm[(size_t)s * n_w + cur[kws[q]]++] = q;
     }
+    sh_mean_s0 = tot / ((double)n_scenes * n_v * n_w);
   }
   // ---- worth it?  Sharing removes the first max(kv, kw) steps of every sample and costs two latency-bound
   // path launches of kmax steps each.  Cost model from scripts/share_probe.py / latency_probe.py (us).

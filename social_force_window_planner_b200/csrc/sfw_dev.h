@@ -86,14 +86,14 @@ struct SfwShareDev {
   uint8_t *records;         // [scene][4 + 2 n_w + 2 n_v paths][kmax + 1 step counts][rec_bytes]
   const uint16_t *kv, *kw;  // [scene][n_v], [scene][n_w]
   const uint8_t *dirv, *dirw; // 1 = ramping up
-  // launch 3 walks the grid in fork-step order (scene 0's tables, any fixed order is correct for the others):
+  // launch 3 walks every scene's grid in its own fork-step order:
   // thread position `pos` -> the pos-th sample when all are sorted by max(kv, kw).  No per-sample table: with
   // rows sorted by kv (row_perm), columns by kw (col_perm) and lvl_rows[k] / lvl_cols[k] = how many rows / columns
   // fork before step k, the samples that fork before step k are the lvl_rows[k] x lvl_cols[k] corner of the sorted
   // grid, and level k itself is (rows of level k) x (columns up to level k) followed by (rows before level k) x
   // (columns of level k).  A warp is therefore 32 samples that fork together whatever the aspect of the grid.
-  const uint32_t *col_perm, *row_perm;
-  const uint32_t *lvl_rows, *lvl_cols; // [kmax + 2]
+  const uint32_t *col_perm, *row_perm; // [scene][n_w], [scene][n_v]
+  const uint32_t *lvl_rows, *lvl_cols; // [scene][kmax + 2]
   // one-wave launches: chunk_map[idx / 32] = which 32 sorted samples warp idx / 32 takes (deals long and short
   // warps evenly over blocks and schedulers); nullptr = identity
   const uint32_t *chunk_map;

@@ -223,25 +223,28 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
       in_range = pos < last;
       if (in_range) {
         // level of pos: the largest k with lvl_rows[k] * lvl_cols[k] <= pos
+        const uint32_t *lvl_rows = H.lvl_rows + (size_t)scene * (H.kmax + 2u);
+        const uint32_t *lvl_cols = H.lvl_cols + (size_t)scene * (H.kmax + 2u);
+        const uint32_t *row_perm = H.row_perm + (size_t)scene * B.n_v, *col_perm = H.col_perm + (size_t)scene * n_w;
         uint32_t lo = 0u, hi = H.kmax + 1u;
         while (hi - lo > 1u) {
           const uint32_t mid = (lo + hi) >> 1;
-          if (H.lvl_rows[mid] * H.lvl_cols[mid] <= pos)
+          if (lvl_rows[mid] * lvl_cols[mid] <= pos)
             lo = mid;
           else
             hi = mid;
         }
-        const uint32_t r0 = H.lvl_rows[lo], r1 = H.lvl_rows[lo + 1u], c0 = H.lvl_cols[lo], c1 = H.lvl_cols[lo + 1u];
+        const uint32_t r0 = lvl_rows[lo], r1 = lvl_rows[lo + 1u], c0 = lvl_cols[lo], c1 = lvl_cols[lo + 1u];
         const uint32_t local = pos - r0 * c0, n_a = (r1 - r0) * c1;
         uint32_t r, c;
         if (local < n_a) { // rows of this level x columns up to this level
           const uint32_t q = local / c1;
-          r = H.row_perm[r0 + q];
-          c = H.col_perm[local - q * c1];
+          r = row_perm[r0 + q];
+          c = col_perm[local - q * c1];
         } else { // earlier rows x columns of this level
           const uint32_t l2 = local - n_a, nc = c1 - c0, q = l2 / nc;
-          r = H.row_perm[q];
-          c = H.col_perm[c0 + (l2 - q * nc)];
+          r = row_perm[q];
+          c = col_perm[c0 + (l2 - q * nc)];
         }
         idx = r * n_w + c;
         v_s = B.linvels[r];
