@@ -464,7 +464,8 @@ def test_prefix_sharing_forced_on_ragged_grids(n_v, n_w, n_scenes, n_peds, group
     counts (a dummy pair half), pedestrian groups (thread-per-path writers instead of warp-per-path)."""
     from social_force_window_planner_b200.scorer import Scorer
     wl = dataclasses.replace(S.WORKLOADS["C1"], n_v=n_v, n_w=n_w, n_peds=n_peds)
-    scs = S.make_scenes(wl, n_scenes)
+    # the last scene has a lethal box ahead and a pedestrian crossing the robot's path: shared paths die too
+    scs = [S.make_scene(wl, i, hazards=(n_scenes > 1 and i == n_scenes - 1)) for i in range(n_scenes)]
     for k, sc in enumerate(scs):
         r = list(sc.robot)
         r[3] = float(np.float32(0.1 + 0.1 * k))
@@ -490,6 +491,8 @@ def test_prefix_sharing_forced_on_ragged_grids(n_v, n_w, n_scenes, n_peds, group
     assert np.array_equal(costs_on, costs_off)
     assert np.array_equal(best_on, best_off)
     assert (costs_on >= 0).any()
+    if n_scenes > 1:
+        assert (costs_on[-1] == -1.0).any(), "the hazards scene should kill trajectories (and shared paths)"
     _spot_check(p, scs[-1], lin, ang, costs_on[-1], [0, n_w + 1, n_v * n_w - 1])
 
 
