@@ -78,3 +78,48 @@ def test_random_scene_latency_policy(seed):
     finally:
         s2.close()
     print(seed, wl.n_peds, "peds", st)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_grid_with_forced_prefix_sharing(seed):
+    """Mid-size random grids with rollout prefix sharing forced on (``set_prefix_sharing(2)``), through the kernel
+    family AUTO picks and through the thread-per-trajectory family: against the oracle, and bit for bit against the
+    same run without sharing.  Random accelerations move the fork steps around; hazards kill shared paths; group
+    tags select the thread-per-path writers, their absence the warp-per-path ones."""
+    from social_force_window_planner_b200.scorer import Scorer
+    rng = SplitMix64(99 + seed)
+    pick = lambda lo, hi: lo + int(rng.uniform() * (hi - lo + 1))  # noqa: E731
+    n_peds = [0, 1, 5, 12, 19, 20, 33, 64][pick(0, 7)]
+    wl = dataclasses.replace(S.WORKLOADS["C0"], n_v=pick(16, 40), n_w=pick(64, 90), steps=pick(12, 40), n_peds=n_peds,
+                             map_w=pick(160, 260), map_h=pick(160, 260), ped_r_max=5.5 if n_peds > 30 else None,
+                             ped_sep=0.5 if n_peds > 30 else 0.8)
+    sc = S.make_scene(wl, 1000 + seed, n_obstacles=pick(0, 40), hazards=rng.uniform() < 0.4)
+    if seed % 3 == 0:
+        for j in range(min(n_peds, 6)):
+            sc.peds[j]["group_id"] = j // 3
+    r = list(sc.robot)
+    r[3] = float(np.float32(rng.uniform(0.0, 0.5)))
+    r[5] = float(np.float32(rng.uniform(-0.5, 0.5)))
+    r[10] = r[3]
+    sc.robot = tuple(r)
+    p = wl.params()
+    p.max_trans_acc = rng.uniform(0.3, 1.5)
+    p.max_rot_acc = rng.uniform(0.3, 1.5)
+    lin, ang = wl.sample_arrays(max_vel_x=rng.uniform(0.5, 1.0), max_vel_th=rng.uniform(0.5, 1.2))
+    p.max_vel_x = float(lin[-1])
+    s2 = Scorer(0)
+    try:
+        for pol in (Scorer.POLICY_AUTO, Scorer.POLICY_THROUGHPUT):
+            s2.set_policy(pol)
+            s2.set_prefix_sharing(2)
+            c_on, b_on = s2.score(p, [sc], lin, ang)
+            k_on = s2.last_kernel
+            s2.set_prefix_sharing(0)
+            c_off, b_off = s2.score(p, [sc], lin, ang)
+            assert "share" in k_on and "share" not in s2.last_kernel, (k_on, s2.last_kernel)
+            assert np.array_equal(c_on, c_off) and np.array_equal(b_on, b_off), k_on
+            if pol == Scorer.POLICY_AUTO:
+                st = parity.compare(p, sc, lin, ang, c_on[0], b_on[0], max_near_frac=1.0)
+    finally:
+        s2.close()
+    print(seed, wl.n_v, "x", wl.n_w, wl.steps, "steps", n_peds, "peds", k_on, st)
