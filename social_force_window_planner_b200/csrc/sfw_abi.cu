@@ -1122,9 +1122,10 @@ int sfw_run(sfw_ctx *c) {
   } else if (re > rb && c->share_active && rb == 0 && re == B.n_v) {
     // rollout prefix sharing: the 4 doubly saturated paths, the 2 (n_v + n_w) singly saturated ones (each
     // continuing one of the 4), then every sample from the record of its own fork point
-    // (the path launches are latency bound: small blocks, so that every scene's few paths are resident at once)
+    // (the path launches are latency bound: small blocks, so that every scene's few paths are resident at once --
+    // but not smaller than 128 threads: the block's prologue, the free-space bit map of the window, is shared work)
     SfwBatchDev W = B;
-    const uint32_t T1 = 32, T2 = 128;
+    const uint32_t T1 = 128, T2 = 128;
     const uint32_t per = SFW_PATH_WARP_THREADS / 32u;
     const size_t smw = sfw_small_smem_bytes(B.win_wp, B.win_h, c->plan.maxP, c->plan.maxM, c->plan.maxF,
                                             SFW_PATH_WARP_THREADS);
