@@ -208,6 +208,15 @@ int sfw_set_policy(sfw_ctx *ctx, int policy);
  * it (grids of >= 1024 samples, >= 8 steps, some saturated ramp; for tests and experiments). */
 int sfw_set_prefix_sharing(sfw_ctx *ctx, int on);
 
+/* Far-field cutoff of the pedestrians' obstacle force (applies from the next sfw_upload).  lightsfm sums
+ * k/M * exp(-(|p - o| - r)/sigma) over every obstacle point o (reached through the
+ * computeForces call at reference src/sfw_planner.cpp:592).  The library stores the points as spatially compact
+ * clusters of 8 and a pedestrian skips a cluster all of whose terms are below 2^-cutoff_log2 of the force factor
+ * k/M.  Default 24 (one FP32 ulp: with sigma = 0.2 m, r = 0.35 m that is > 3.7 m away); <= 0 switches the
+ * cutoff off (every term is summed).  The robot's own obstacle force, which enters the social work directly,
+ * always sums every point. */
+int sfw_set_obstacle_cutoff(sfw_ctx *ctx, double cutoff_log2);
+
 /* Restrict the next sfw_run calls to linvel rows [row_begin, row_end) of every staged scene
  * (multi-GPU sharding of a single scene across ranks: each rank scores a slab and the winners
  * are all-gathered by the caller).  Rows outside the slab get SFW_COST_SKIPPED. */
@@ -292,6 +301,10 @@ const char *sfw_last_kernel(const sfw_ctx *ctx);
 /* rollout prefix sharing of the staged batch: mean number of leading steps a sample takes from a shared path
  * instead of simulating them itself (0 when sharing is off for this batch) */
 double sfw_shared_prefix_steps(const sfw_ctx *ctx);
+/* obstacle far-field cutoff of the staged batch: fraction of (pedestrian, obstacle cluster) combinations that
+ * are out of reach at the pedestrians' START positions (an estimate of the skipped share of the obstacle sums;
+ * 0 when the cutoff is off or there are no obstacles) */
+double sfw_obstacle_skip_fraction(const sfw_ctx *ctx);
 
 #ifdef __cplusplus
 }

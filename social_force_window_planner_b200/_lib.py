@@ -21,6 +21,7 @@ EXPORTS = [
     "sfw_device_costs", "sfw_device_best", "sfw_kernel_launches", "sfw_algorithmic_bytes",
     "sfw_last_kernel", "sfw_shared_prefix_steps", "sfw_h2d_bytes", "sfw_d2h_bytes", "sfw_laser_obstacles", "sfw_marker_points", "sfw_exchange_export", "sfw_exchange_connect",
     "sfw_exchange_sync", "sfw_exchange_fetch", "sfw_exchange_device_buffer", "sfw_set_policy", "sfw_set_prefix_sharing", "sfw_may_i_stop",
+    "sfw_set_obstacle_cutoff", "sfw_obstacle_skip_fraction",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -103,6 +104,10 @@ def load() -> C.CDLL:
     lib.sfw_last_kernel.argtypes = [_ctx]
     lib.sfw_shared_prefix_steps.restype = C.c_double
     lib.sfw_shared_prefix_steps.argtypes = [_ctx]
+    lib.sfw_set_obstacle_cutoff.restype = C.c_int
+    lib.sfw_set_obstacle_cutoff.argtypes = [_ctx, C.c_double]
+    lib.sfw_obstacle_skip_fraction.restype = C.c_double
+    lib.sfw_obstacle_skip_fraction.argtypes = [_ctx]
     return lib
 
 

@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -219,6 +220,68 @@ int make_plan(sfw_ctx *c, uint32_t n_scenes, uint32_t samples, uint32_t P, uint3
   return SFW_OK;
 }
 
+
+// Obstacle points -> clusters of 8 behind a {centre, reach^2} header (sfw_dev.h, obstacle_sum2).  `pts` are in
+// the kernel's units (metres * log2(e)/sigma, scene frame).  Clusters come from recursive median splits along
+// the wider axis, cut at multiples of 8, ties broken by the other coordinate and the input position, so the
+// layout only depends on the points.  reach = cluster radius + r_max (largest agent radius, same units) +
+// cutoff: beyond it every term exp2(-(|p - o| - r)) of the cluster is below 2^-cutoff.  cutoff <= 0: reach = inf.
+void split_obstacles(std::vector<uint32_t> &idx, const std::vector<float2> &pts, size_t lo, size_t hi) {
+  const size_t n = hi - lo;
+  if (n <= SFW_OBST_CLUSTER)
+    return;
+  float x0 = pts[idx[lo]].x, x1 = x0, y0 = pts[idx[lo]].y, y1 = y0;
+  for (size_t i = lo; i < hi; ++i) {
+    const float2 p = pts[idx[i]];
+    x0 = std::min(x0, p.x), x1 = std::max(x1, p.x), y0 = std::min(y0, p.y), y1 = std::max(y1, p.y);
+  }
+  const bool along_x = (x1 - x0) >= (y1 - y0);
+  std::sort(idx.begin() + lo, idx.begin() + hi, [&](uint32_t a, uint32_t b) {
+    const float2 p = pts[a], q = pts[b];
+    const float pa = along_x ? p.x : p.y, qa = along_x ? q.x : q.y;
+    if (pa != qa)
+      return pa < qa;
+    const float pb = along_x ? p.y : p.x, qb = along_x ? q.y : q.x;
+    if (pb != qb)
+      return pb < qb;
+    return a < b;
+  });
+  const size_t clusters = (n + SFW_OBST_CLUSTER - 1) / SFW_OBST_CLUSTER;
+  const size_t mid = lo + SFW_OBST_CLUSTER * ((clusters + 1) / 2);
+  split_obstacles(idx, pts, lo, mid);
+  split_obstacles(idx, pts, mid, hi);
+}
+
+void pack_obstacles(const std::vector<float2> &pts, float2 *out, double cutoff_log2, double r_max) {
+  const size_t n = pts.size();
+  std::vector<uint32_t> idx(n);
+  for (size_t i = 0; i < n; ++i)
+    idx[i] = (uint32_t)i;
+  split_obstacles(idx, pts, 0, n);
+  for (size_t lo = 0, g = 0; lo < n; lo += SFW_OBST_CLUSTER, ++g) {
+    const size_t hi = std::min(n, lo + SFW_OBST_CLUSTER);
+    float2 *rec = out + g * SFW_OBST_CLUSTER_SLOTS;
+    float x0 = pts[idx[lo]].x, x1 = x0, y0 = pts[idx[lo]].y, y1 = y0;
+    for (size_t i = lo; i < hi; ++i) {
+      const float2 p = pts[idx[i]];
+      x0 = std::min(x0, p.x), x1 = std::max(x1, p.x), y0 = std::min(y0, p.y), y1 = std::max(y1, p.y);
+    }
+    const float cx = 0.5f * (x0 + x1), cy = 0.5f * (y0 + y1);
+    double rad = 0.0;
+    for (size_t i = lo; i < hi; ++i)
+      rad = std::max(rad, std::hypot((double)pts[idx[i]].x - cx, (double)pts[idx[i]].y - cy));
+    float reach2 = std::numeric_limits<float>::infinity();
+    if (cutoff_log2 > 0.0) {
+      const double reach = (rad + r_max + cutoff_log2) * (1.0 + 1e-6); // rounding of the device's FP32 test
+      const double r2 = reach * reach;
+      reach2 = r2 < 3.0e38 ? (float)r2 : std::numeric_limits<float>::infinity();
+    }
+    rec[0] = make_float2(cx, cy);
+    rec[1] = make_float2(reach2, 0.f);
+    for (size_t i = 0; i < SFW_OBST_CLUSTER; ++i)
+      rec[2 + i] = (lo + i < hi) ? pts[idx[lo + i]] : make_float2(SFW_FAR_AWAY, 0.f);
+  }
+}
 } // namespace
 
 extern "C" {
@@ -289,7 +352,7 @@ int sfw_create(sfw_ctx **out, int device, void *stream, const SfwLimits *limits)
   if (limits) {
     size_t in_est = (size_t)limits->max_scenes *
                         (sizeof(SfwSceneDev) + (size_t)limits->max_peds * 48 +
-                         (size_t)limits->max_obstacles * 8 + 1024 + align_up(limits->max_cells, 256)) +
+                         (size_t)sfw_obst_slots(limits->max_obstacles) * 8 + 1024 + align_up(limits->max_cells, 256)) +
                     65536;
     size_t out_est = (size_t)limits->max_scenes * (sizeof(SfwBest) + (size_t)limits->max_samples * 6 + 4096);
     if (arena_reserve(c, c->in, in_est) != SFW_OK || arena_reserve(c, c->out, out_est) != SFW_OK) {
@@ -380,8 +443,85 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     max_sx = std::max(max_sx, sc.size_x);
     max_sy = std::max(max_sy, sc.size_y);
     totP += (sc.n_peds + 1) / 2;         // pedestrians are stored as pairs
-    totM += align_up(sc.n_obstacles, 2); // obstacle lists are padded to an even count
+    totM += sfw_obst_slots(sc.n_obstacles); // clusters of 8 points behind a 2-slot header (sfw_dev.h)
     totF += sc.n_footprint;
+  }
+
+  // ---- obstacle clusters, and the pedestrian order that goes with them -------------------------
+  // Obstacle points are stored as compact clusters a pedestrian PAIR skips when both members are out of reach
+  // (obstacle_sum2).  Pedestrians are therefore packed in the order of the clusters they reach from their start
+  // positions, so that the two members of a pair (and neighbouring pairs: the lanes of the block-per-trajectory
+  // kernel) skip the same clusters.  Any order is a valid one: the social force sums over all others.
+  std::vector<float2> obs_packed(totM);
+  std::vector<uint32_t> ped_order, ped_slot; // packed position -> caller's index, and back (flat over scenes)
+  std::vector<uint32_t> ped_first(n_scenes + 1, 0);
+  uint64_t cull_skipped = 0, cull_tests = 0;
+  {
+    uint64_t totPeds = 0;
+    for (uint32_t s = 0; s < n_scenes; ++s)
+      totPeds += scenes[s].n_peds;
+    ped_order.resize(totPeds);
+    ped_slot.resize(totPeds);
+    const double c_obs_d = (double)(float)(1.4426950408889634 / sfm.force_sigma_obstacle);
+    std::vector<float2> pts;
+    std::vector<uint64_t> reach; // per pedestrian: bit g = cluster g within reach, words_per pedestrian
+    std::vector<uint32_t> reach_n;
+    size_t pM = 0, pJ = 0;
+    for (uint32_t s = 0; s < n_scenes; ++s) {
+      const SfwScene &sc = scenes[s];
+      const SfwRobot &R = sc.robot;
+      ped_first[s] = (uint32_t)pJ;
+      float r_max = (float)R.agent_radius;
+      for (uint32_t j = 0; j < sc.n_peds; ++j)
+        r_max = std::max(r_max, (float)sc.peds[j].radius);
+      pts.resize(sc.n_obstacles);
+      for (uint32_t k = 0; k < sc.n_obstacles; ++k)
+        pts[k] = make_float2((float)((sc.obstacles_xy[2 * k] - R.x) * c_obs_d),
+                             (float)((sc.obstacles_xy[2 * k + 1] - R.y) * c_obs_d));
+      float2 *rec = obs_packed.data() + pM;
+      pack_obstacles(pts, rec, c->obst_cutoff_log2, (double)r_max * c_obs_d);
+      const uint32_t slots = sfw_obst_slots(sc.n_obstacles), n_cl = slots / SFW_OBST_CLUSTER_SLOTS;
+      uint32_t *order = ped_order.data() + pJ;
+      for (uint32_t j = 0; j < sc.n_peds; ++j)
+        order[j] = j;
+      if (c->obst_cutoff_log2 > 0.0 && n_cl && sc.n_peds) {
+        const uint32_t words = (n_cl + 63u) / 64u;
+        reach.assign((size_t)sc.n_peds * words, 0ull);
+        reach_n.assign(sc.n_peds, 0u);
+        for (uint32_t j = 0; j < sc.n_peds; ++j) {
+          const float qx = (float)(sc.peds[j].x - R.x) * (float)c_obs_d, qy = (float)(sc.peds[j].y - R.y) * (float)c_obs_d;
+          for (uint32_t g = 0; g < n_cl; ++g) {
+            const float dx = qx - rec[g * SFW_OBST_CLUSTER_SLOTS].x, dy = qy - rec[g * SFW_OBST_CLUSTER_SLOTS].y;
+            if (dx * dx + dy * dy <= rec[g * SFW_OBST_CLUSTER_SLOTS + 1].x) {
+              reach[(size_t)j * words + g / 64u] |= 1ull << (g & 63u);
+              ++reach_n[j];
+            }
+          }
+        }
+        std::sort(order, order + sc.n_peds, [&](uint32_t a, uint32_t b) {
+          if (reach_n[a] != reach_n[b])
+            return reach_n[a] > reach_n[b];
+          for (uint32_t w = 0; w < words; ++w)
+            if (reach[(size_t)a * words + w] != reach[(size_t)b * words + w])
+              return reach[(size_t)a * words + w] < reach[(size_t)b * words + w];
+          return a < b;
+        });
+        // share of (pair, cluster) tests that skip the cluster at the start positions (reported only)
+        for (uint32_t k = 0; k < sc.n_peds; k += 2) {
+          const uint32_t a = order[k], b = (k + 1 < sc.n_peds) ? order[k + 1] : order[k];
+          for (uint32_t w = 0; w < words; ++w) {
+            const uint64_t either = reach[(size_t)a * words + w] | reach[(size_t)b * words + w];
+            cull_skipped += (w + 1 < words ? 64u : n_cl - 64u * w) - (uint32_t)__builtin_popcountll(either);
+          }
+          cull_tests += n_cl;
+        }
+      }
+      for (uint32_t j = 0; j < sc.n_peds; ++j)
+        ped_slot[pJ + order[j]] = j;
+      pM += slots;
+      pJ += sc.n_peds;
+    }
+    ped_first[n_scenes] = (uint32_t)pJ;
   }
 
   // ---- pedestrian groups: lightsfm only applies group forces to groups with >= 2 members ------
@@ -408,7 +548,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
             const float rad = (float)sc.peds[tagged[m].second].radius;
             uint32_t bits;
             memcpy(&bits, &rad, 4);
-            members.push_back(tagged[m].second);
+            members.push_back(ped_slot[ped_first[s] + tagged[m].second]); // index in the packed order
             members.push_back(bits);
           }
         }
@@ -800,7 +940,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     d.win_x0 = wx0[s];
     d.win_y0 = wy0[s];
     const uint32_t n_pairs = (sc.n_peds + 1) / 2;
-    const uint32_t n_obst_pad = (uint32_t)align_up(sc.n_obstacles, 2);
+    const uint32_t n_obst_pad = sfw_obst_slots(sc.n_obstacles);
     d.n_peds = sc.n_peds;
     d.n_pairs = n_pairs;
     d.n_obst = n_obst_pad;
@@ -827,7 +967,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
         const uint32_t j = 2 * k + hlf;
         float *v = q[hlf];
         if (j < sc.n_peds) {
-          const SfwPed &p = sc.peds[j];
+          const SfwPed &p = sc.peds[ped_order[ped_first[s] + j]];
           v[0] = (float)(p.x - R.x);
           v[1] = (float)(p.y - R.y);
           v[2] = (float)p.vx;
@@ -854,12 +994,8 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
       hPar2[pP + k] = make_float4(q[0][8], q[1][8], q[0][9], q[1][9]);
     }
     pP += n_pairs;
-    // obstacle points: scene frame, pre-multiplied by log2(e)/sigma (see obstacle_sum2)
-    for (uint32_t k = 0; k < sc.n_obstacles; ++k)
-      hO[pM + k] = make_float2((float)((sc.obstacles_xy[2 * k] - R.x) * c_obs_d),
-                               (float)((sc.obstacles_xy[2 * k + 1] - R.y) * c_obs_d));
-    if (sc.n_obstacles & 1u)
-      hO[pM + sc.n_obstacles] = make_float2(SFW_FAR_AWAY, 0.f);
+    // obstacle points: scene frame, pre-multiplied by log2(e)/sigma, clustered (packed above)
+    memcpy(hO + pM, obs_packed.data() + pM, sizeof(float2) * n_obst_pad);
     pM += n_obst_pad;
     for (uint32_t k = 0; k < sc.n_footprint; ++k)
       hF[pF + k] = make_double2(sc.footprint_xy[2 * k], sc.footprint_xy[2 * k + 1]);
@@ -991,6 +1127,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     c->share_paths = share_paths;
     c->share_mean_s0 = sh_mean_s0;
   }
+  c->obst_skip_frac = cull_tests ? (double)cull_skipped / (double)cull_tests : 0.0;
   if (win_wp) {
     rc = make_tensor_map(c, B.maps, map_pitch, map_rows, n_scenes, win_wp, win_h);
     if (rc != SFW_OK)
@@ -1019,6 +1156,16 @@ int sfw_set_policy(sfw_ctx *c, int policy) {
     return fail(c, SFW_ERR_ARG, "sfw_set_policy: unknown policy %d", policy);
   c->policy = policy;
   c->plan.valid = false;
+  return SFW_OK;
+}
+
+int sfw_set_obstacle_cutoff(sfw_ctx *c, double cutoff_log2) {
+  if (!c)
+    return SFW_ERR_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (cutoff_log2 != cutoff_log2)
+    return fail(c, SFW_ERR_ARG, "sfw_set_obstacle_cutoff: NaN");
+  c->obst_cutoff_log2 = cutoff_log2;
   return SFW_OK;
 }
 
@@ -1330,6 +1477,7 @@ uint64_t sfw_d2h_bytes(const sfw_ctx *c) {
   return (c && c->staged) ? (sizeof(SfwBest) + 4ull * c->out_samples) * c->B.n_scenes : 0;
 }
 const char *sfw_last_kernel(const sfw_ctx *c) { return c ? c->last_kernel : "none"; }
+double sfw_obstacle_skip_fraction(const sfw_ctx *c) { return (c && c->staged) ? c->obst_skip_frac : 0.0; }
 double sfw_shared_prefix_steps(const sfw_ctx *c) { return (c && c->share_active) ? c->share_mean_s0 : 0.0; }
 
 } // extern "C"

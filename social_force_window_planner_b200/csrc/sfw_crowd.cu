@@ -81,7 +81,7 @@ __device__ __forceinline__ CrowdSmem carve(unsigned char *base, uint32_t P2, uin
 } // namespace
 
 size_t sfw_crowd_smem_bytes(uint32_t P, uint32_t M, uint32_t F, uint32_t S) {
-  const size_t P2 = (P + 1u) / 2u, Mp = (M + 1u) & ~1u;
+  const size_t P2 = (P + 1u) / 2u, Mp = sfw_obst_slots(M);
   auto r = [](size_t b) { return (b + 15u) & ~(size_t)15u; };
   return 5 * r(16 * P2) + r(16 * P2 * kCrowdWarps) + r(8 * Mp) + r(16 * (size_t)F) + 5 * r(8 * ((size_t)S + 1)) +
          r(4 * ((size_t)S + 1)) + r(4 * (size_t)S) + r(2 * P2) + r(16 * kCrowdWarps) + 16;

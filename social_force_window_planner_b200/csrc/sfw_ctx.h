@@ -44,6 +44,8 @@ struct sfw_ctx {
   SfwArena sensor_in, sensor_out; // sfw_laser_obstacles / sfw_marker_points staging
   bool laser_attr_set = false;
   int policy = 0; // SFW_POLICY_*
+  double obst_cutoff_log2 = SFW_OBST_CUTOFF_LOG2; // sfw_set_obstacle_cutoff; <= 0: off
+  double obst_skip_frac = 0.0;                    // of the staged batch, at the start poses
 
   // rollout prefix sharing (SfwShareDev)
   int share_allowed = 1;      // sfw_set_prefix_sharing: 0 never, 1 when the cost model says it pays, 2 whenever possible

@@ -23,6 +23,18 @@
 #define SFW_MAX_BLOCK_SMALL 512 /* launch bound of the thread-per-trajectory kernel (128 regs/thread) */
 #define SFW_PATH_WARP_THREADS 128 /* block of the warp-per-path record writer: 4 paths */
 
+// Obstacle points are stored as spatially compact CLUSTERS of 8 (sfw_abi.cu: pack_obstacles): 10 float2 slots
+// per cluster = {centre x, centre y}, {reach^2, unused}, then the 8 points (the last cluster padded with
+// SFW_FAR_AWAY points).  All in the obstacle_sum2 units (metres * log2(e)/sigma).  A pedestrian whose squared
+// distance to the centre exceeds reach^2 = (cluster radius + largest pedestrian radius + cutoff)^2 skips the
+// cluster: every term of it is below 2^-cutoff of the force factor.
+#define SFW_OBST_CLUSTER 8
+#define SFW_OBST_CLUSTER_SLOTS 10
+#define SFW_OBST_CUTOFF_LOG2 24.0 /* default cutoff: terms below 2^-24 (one FP32 ulp of the factor) */
+static inline uint32_t sfw_obst_slots(uint32_t n_points) {
+  return SFW_OBST_CLUSTER_SLOTS * ((n_points + SFW_OBST_CLUSTER - 1u) / SFW_OBST_CLUSTER);
+}
+
 struct SfwSceneDev {
   // robot rollout start (FP64 world frame) — SfwRobot
   double rx, ry, rth, rvx, rvy, rvth;
@@ -34,7 +46,7 @@ struct SfwSceneDev {
   float a_obs_scale; // (k_obs / M) * exp(agent_radius / sigma)
   uint32_t size_x, size_y;
   int32_t win_x0, win_y0; // first cell of the staged window (may be negative / beyond the map)
-  uint32_t n_peds, n_obst, n_fp; // n_obst: padded to an even count with a far-away point
+  uint32_t n_peds, n_obst, n_fp; // n_obst: float2 SLOTS of the clustered obstacle list (sfw_obst_slots)
   uint32_t ped_off, obs_off, fp_off; // element offsets into the packed arrays (ped_off in PAIRS)
   uint32_t n_pairs;                  // ceil(n_peds / 2); an odd crowd is padded with a far-away agent
   uint64_t map_off; // byte offset of this scene's costmap slot

@@ -289,8 +289,9 @@ __device__ __forceinline__ void pair_force2(const SfmConst &K, f2 ax, f2 ay, f2 
 
 // lightsfm obstacle force sum (unscaled): sum_o exp(-|p-o|/sigma) (p-o)/|p-o|.  Obstacle points are
 // stored pre-multiplied by c_obs = log2(e)/sigma, and so is the query point: then |p'-o'| is the
-// exponent in log2 units and the unit vector is unchanged.  The list is padded to an even count
-// with a point 1e15 away, whose term is exactly 0 (ex2 underflows).
+// exponent in log2 units and the unit vector is unchanged.  The list comes as clusters of 8 points behind
+// a 2-slot header {centre, reach^2} (sfw_dev.h); the last cluster is padded with points 1e15 away, whose
+// term is exactly 0 (ex2 underflows).  `M` counts float2 SLOTS (10 per cluster).
 // one obstacle point against the two pedestrians of a pair
 __device__ __forceinline__ void obstacle_term2(float2 p, f2 qx, f2 qy, f2 &ax, f2 &ay) {
   const f2 dx = sub2(qx, bc2(p.x)), dy = sub2(qy, bc2(p.y));
@@ -303,42 +304,51 @@ __device__ __forceinline__ void obstacle_term2(float2 p, f2 qx, f2 qy, f2 &ax, f
   ay = fma2(e, dy, ay);
 }
 
-// (a) two query points (a pedestrian pair) against every obstacle, 8 points per trip (the loop is
-// instruction bound: a software exponential on the FMA pipe for some of the points made it slower,
-// DESIGN.md 4.4)
+// (a) two query points (a pedestrian pair) against every obstacle, one cluster of 8 points per trip (the
+// loop is instruction bound: a software exponential on the FMA pipe for some of the points made it slower,
+// DESIGN.md 4.4).  A cluster out of reach of BOTH pedestrians is skipped.  The test only reads the thread's
+// own pair, so the result does not depend on which trajectories share a warp (prefix sharing and the
+// warp-per-path writers stay bit-identical); pedestrians are within millimetres of each other across the
+// trajectories of a warp, so the branch is uniform in practice.
 __device__ __forceinline__ void obstacle_sum2(const float2 *__restrict__ obs, int M, float c_obs, f2 px,
                                               f2 py, f2 &sx, f2 &sy) {
   f2 ax = bc2(0.f), ay = bc2(0.f);
   const f2 qx = mul2(px, bc2(c_obs)), qy = mul2(py, bc2(c_obs));
-  int o = 0;
-  for (; o + 8 <= M; o += 8) {
+  for (int o = 0; o < M; o += SFW_OBST_CLUSTER_SLOTS) {
+    const float4 hd = *reinterpret_cast<const float4 *>(obs + o);
+    const f2 cx = sub2(qx, bc2(hd.x)), cy = sub2(qy, bc2(hd.y));
+    float c0, c1;
+    un2(fma2(cx, cx, mul2(cy, cy)), c0, c1);
+    if (fminf(c0, c1) <= hd.z) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      obstacle_term2(obs[o + i], qx, qy, ax, ay);
+      for (int i = 0; i < SFW_OBST_CLUSTER; ++i)
+        obstacle_term2(obs[o + 2 + i], qx, qy, ax, ay);
+    }
   }
-  for (; o < M; ++o)
-    obstacle_term2(obs[o], qx, qy, ax, ay);
   sx = ax;
   sy = ay;
 }
-// (b) one query point (the robot) against two obstacles per iteration
+// (b) one query point (the robot) against two obstacles per iteration; never skips a cluster (the robot's
+// obstacle force goes into the social work as it is)
 __device__ __forceinline__ void obstacle_sum1(const float2 *__restrict__ obs, int M, float c_obs,
                                               float px, float py, float &sx, float &sy) {
   f2 ax = bc2(0.f), ay = bc2(0.f);
   const f2 eps = bc2(1e-30f);
   const f2 qx = bc2(px * c_obs), qy = bc2(py * c_obs);
-  const float4 *__restrict__ obs4 = reinterpret_cast<const float4 *>(obs);
-#pragma unroll 2
-  for (int o = 0; o < M / 2; ++o) {
-    const float4 p = obs4[o];
-    const f2 dx = sub2(qx, mk2(p.x, p.z)), dy = sub2(qy, mk2(p.y, p.w));
-    const f2 d2 = fma2(dx, dx, fma2(dy, dy, eps));
-    const f2 rd = rsqrt2(d2);
-    float d0, d1;
-    un2(mul2(d2, rd), d0, d1);
-    const f2 e = mul2(mk2(ex2_approx(-d0), ex2_approx(-d1)), rd);
-    ax = fma2(e, dx, ax);
-    ay = fma2(e, dy, ay);
+  for (int o = 0; o < M; o += SFW_OBST_CLUSTER_SLOTS) {
+    const float4 *__restrict__ obs4 = reinterpret_cast<const float4 *>(obs + o + 2);
+#pragma unroll
+    for (int i = 0; i < SFW_OBST_CLUSTER / 2; ++i) {
+      const float4 p = obs4[i];
+      const f2 dx = sub2(qx, mk2(p.x, p.z)), dy = sub2(qy, mk2(p.y, p.w));
+      const f2 d2 = fma2(dx, dx, fma2(dy, dy, eps));
+      const f2 rd = rsqrt2(d2);
+      float d0, d1;
+      un2(mul2(d2, rd), d0, d1);
+      const f2 e = mul2(mk2(ex2_approx(-d0), ex2_approx(-d1)), rd);
+      ax = fma2(e, dx, ax);
+      ay = fma2(e, dy, ay);
+    }
   }
   float x0, x1, y0, y1;
   un2(ax, x0, x1);

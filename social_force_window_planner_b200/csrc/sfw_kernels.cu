@@ -87,7 +87,7 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   float4 *s_par2 = reinterpret_cast<float4 *>(smem_raw + off);
   off += P2 * 16u;
   float2 *s_obs = reinterpret_cast<float2 *>(smem_raw + off);
-  off += M * 8u; // M is even
+  off += M * 8u; // M counts float2 slots: a multiple of 10
   double2 *s_fp = reinterpret_cast<double2 *>(smem_raw + off);
   off += F * 16u;
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + off);
@@ -967,7 +967,7 @@ extern "C" __global__ void sfw_may_i_stop_kernel(const __grid_constant__ SfwBatc
 // ================================================================================================
 size_t sfw_small_smem_bytes(uint32_t win_wp, uint32_t win_h, uint32_t P, uint32_t M, uint32_t F, uint32_t T) {
   const uint32_t win_bytes = win_wp * win_h;
-  const size_t P2 = (P + 1u) / 2u, Mp = (M + 1u) & ~1u;
+  const size_t P2 = (P + 1u) / 2u, Mp = sfw_obst_slots(M);
   size_t off = (win_bytes + 127u) & ~127u;
   off += 5u * P2 * 16u;
   off += Mp * 8u;

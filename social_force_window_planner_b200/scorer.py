@@ -75,6 +75,12 @@ class Scorer:
         True / 1 = when the library's cost model says it pays, 2 = whenever the batch allows it."""
         self._check(self._lib.sfw_set_prefix_sharing(self._ctx, int(on)))
 
+    def set_obstacle_cutoff(self, cutoff_log2: float):
+        """Far-field cutoff of the pedestrians' obstacle force (``sfw_set_obstacle_cutoff``): clusters of obstacle
+        points whose every term is below ``2**-cutoff_log2`` of the force factor are skipped.  Default 24; <= 0
+        sums every term.  Applies from the next upload."""
+        self._check(self._lib.sfw_set_obstacle_cutoff(self._ctx, float(cutoff_log2)))
+
     def set_row_slab(self, row_begin: int, row_end: int):
         self._check(self._lib.sfw_set_row_slab(self._ctx, row_begin, row_end))
 
@@ -216,6 +222,11 @@ class Scorer:
     @property
     def last_kernel(self) -> str:
         return self._lib.sfw_last_kernel(self._ctx).decode()
+
+    @property
+    def obstacle_skip_fraction(self) -> float:
+        """Share of (pedestrian, obstacle cluster) combinations out of reach at the start poses of the staged batch."""
+        return float(self._lib.sfw_obstacle_skip_fraction(self._ctx))
 
     @property
     def shared_prefix_steps(self) -> float:
