@@ -345,6 +345,7 @@ def main():
         costs_dev, best_dev = scorer.download()
         kernel_name = scorer.last_kernel
         shared_steps = scorer.shared_prefix_steps
+        obst_skip = scorer.obstacle_skip_fraction
         shared_kmax = min(wl.steps, 2.0 * shared_steps)  # estimate of a shared path's length (the longest ramp)
         algo_bytes = scorer.algorithmic_bytes
 
@@ -399,8 +400,10 @@ def main():
         # pedestrian update (goal direction, speed cap), one extra robot-pedestrian pass after the last step.
         # With rollout prefix sharing a sample does not execute its first `shared` steps (mean over the grid, from
         # the library); the shared paths themselves add 2 (n_v + n_w) + 4 path-prefixes, counted too.
+        # Obstacle clusters a pedestrian pair skips (far-field cutoff) are not executed: the library's skip
+        # fraction at the pedestrians' start positions stands in for the whole rollout (the robot never skips).
         P_, M_, S_ = wl.n_peds, wl.n_obstacles, wl.steps
-        per_step = 4 * (P_ * (P_ - 1) // 2 + P_) + P_ + 2 * (P_ + 1) * M_ + 2 * P_
+        per_step = 4 * (P_ * (P_ - 1) // 2 + P_) + P_ + 2 * (P_ * (1.0 - obst_skip) + 1) * M_ + 2 * P_
         path_steps = (2 * (wl.n_v + wl.n_w) + 4) * shared_kmax / wl.samples if shared_steps > 0 else 0.0
         mufu_exec = (S_ - shared_steps + path_steps) * per_step + 5 * P_
         mufu_per_s = mufu_exec * wl.samples / (k_ms * 1e-3)
@@ -423,6 +426,10 @@ def main():
                                "note": "samples whose velocity ramps are still saturated start from the record of a "
                                        "shared path (bit-identical to the unshared run); kernel_ms covers the path "
                                        "launches and the sample launch"},
+            "obstacle_cutoff": {"skip_fraction_at_start": obst_skip,
+                                "note": "pedestrian pairs skip obstacle clusters whose every term is below 2^-24 of the "
+                                        "force factor (sfw_set_obstacle_cutoff; on-vs-off cost difference about 1e-7 "
+                                        "relative, tests/test_gpu_obstacle_cutoff.py)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo_bytes),
@@ -433,7 +440,7 @@ def main():
                       "model": "reference work (SURVEY.md 8d): S*[N(N-1)+(N-1)] pair + S*N*M obstacle evaluations per "
                                "trajectory (all S steps, as the reference computes them); MUFU count: what the kernels "
                                "execute (each unordered pair once, 4 MUFU; obstacle term 2 MUFU; steps taken from a shared "
-                               "path are not counted) against 16 MUFU/clk/SM at the sampled SM clock"},
+                               "path and obstacle clusters skipped by the far-field cutoff are not counted) against 16 MUFU/clk/SM at the sampled SM clock"},
             "clocks": ck,
             "winner": {"valid": int(best_dev[0]["valid"]), "index": int(best_dev[0]["index"]),
                        "v": float(best_dev[0]["v"]), "w": float(best_dev[0]["w"]), "cost": float(best_dev[0]["cost"])},

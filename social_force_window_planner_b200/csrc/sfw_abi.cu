@@ -236,12 +236,14 @@ void split_obstacles(std::vector<uint32_t> &idx, const std::vector<float2> &pts,
     x0 = std::min(x0, p.x), x1 = std::max(x1, p.x), y0 = std::min(y0, p.y), y1 = std::max(y1, p.y);
   }
   const bool along_x = (x1 - x0) >= (y1 - y0);
+  // NaN coordinates (a caller's problem, but not a reason for an invalid comparator) sort last
+  auto key = [](float v) { return v == v ? v : std::numeric_limits<float>::infinity(); };
   std::sort(idx.begin() + lo, idx.begin() + hi, [&](uint32_t a, uint32_t b) {
     const float2 p = pts[a], q = pts[b];
-    const float pa = along_x ? p.x : p.y, qa = along_x ? q.x : q.y;
+    const float pa = key(along_x ? p.x : p.y), qa = key(along_x ? q.x : q.y);
     if (pa != qa)
       return pa < qa;
-    const float pb = along_x ? p.y : p.x, qb = along_x ? q.y : q.x;
+    const float pb = key(along_x ? p.y : p.x), qb = key(along_x ? q.y : q.x);
     if (pb != qb)
       return pb < qb;
     return a < b;

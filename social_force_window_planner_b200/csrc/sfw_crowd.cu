@@ -312,6 +312,15 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
     const bool even = P2 >= 2u && (P2 & 1u) == 0u; // + the opposite pair, first half of the ring only
     const uint32_t owned = (P2 + kCrowdThreads - 1u) / kCrowdThreads;
     float4 *myrow = sm.frc + warp * P2;
+    // Obstacle sums of the pedestrians: with at most 128 pairs the warps beyond the first `pair_warps` own no pair
+    // and would idle through the force phase.  They take the obstacle clusters instead — helper h of pair a sums
+    // the clusters h, h + n_help, ... into its own warp's accumulator row — so the sums run beside the pair forces
+    // instead of after them (a tick at the reference's 5 x 9 samples is one wave of this kernel: latency is all
+    // there is).  The split only depends on the crowd size, never on the batch or on prefix sharing.
+    const uint32_t pair_warps = (P2 + 31u) >> 5;
+    const uint32_t n_help = (P2 && 2u * pair_warps <= (uint32_t)kCrowdWarps) ? (uint32_t)kCrowdWarps / pair_warps - 1u : 0u;
+    const uint32_t help_idx = n_help ? tid / (32u * pair_warps) : 0u; // 0: the threads that own the pairs
+    const uint32_t help_pair = n_help ? tid - help_idx * 32u * pair_warps : 0u;
     int steps_done = 0;
     bool collided = false;
     if (rec_in) { // the shared path's bookkeeping at this item's fork point
@@ -416,12 +425,14 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
           un2(s0y, l0, h0);
           un2(s1y, l1, h1);
           FY = add2(FY, mk2(l0 + h0, l1 + h1));
-          f2 ox, oy;
-          obstacle_sum2(sm.obs, (int)M, B.c_obs, mk2(pa.x, pa.y), mk2(pa.z, pa.w), ox, oy);
-          const float4 Pc = sm.par2[a];
-          const f2 OS = mk2(Pc.x, Pc.y);
-          FX = fma2(OS, ox, FX);
-          FY = fma2(OS, oy, FY);
+          if (!n_help) {
+            f2 ox, oy;
+            obstacle_sum2(sm.obs, (int)M, B.c_obs, mk2(pa.x, pa.y), mk2(pa.z, pa.w), ox, oy);
+            const float4 Pc = sm.par2[a];
+            const f2 OS = mk2(Pc.x, Pc.y);
+            FX = fma2(OS, ox, FX);
+            FY = fma2(OS, oy, FY);
+          }
           const float4 own = myrow[a];
           float x0, x1, y0, y1;
           un2(add2(mk2(own.x, own.y), FX), x0, x1);
@@ -429,6 +440,18 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
           myrow[a] = make_float4(x0, x1, y0, y1);
         }
         __syncwarp();
+      }
+      if (help_idx >= 1u && help_idx <= n_help && help_pair < P2 && M) {
+        const float4 pa = sm.pos[help_pair];
+        f2 ox, oy;
+        obstacle_sum2(sm.obs, (int)M, B.c_obs, mk2(pa.x, pa.y), mk2(pa.z, pa.w), ox, oy, (int)help_idx - 1, (int)n_help);
+        const float4 Pc = sm.par2[help_pair];
+        const f2 OS = mk2(Pc.x, Pc.y);
+        const float4 own = myrow[help_pair];
+        float x0, x1, y0, y1;
+        un2(fma2(OS, ox, mk2(own.x, own.y)), x0, x1);
+        un2(fma2(OS, oy, mk2(own.z, own.w)), y0, y1);
+        myrow[help_pair] = make_float4(x0, x1, y0, y1);
       }
       {
         float l, h;

@@ -310,11 +310,12 @@ __device__ __forceinline__ void obstacle_term2(float2 p, f2 qx, f2 qy, f2 &ax, f
 // own pair, so the result does not depend on which trajectories share a warp (prefix sharing and the
 // warp-per-path writers stay bit-identical); pedestrians are within millimetres of each other across the
 // trajectories of a warp, so the branch is uniform in practice.
+// `first` / `stride` (in clusters): the block-per-trajectory kernel deals the clusters of a pair over helper threads.
 __device__ __forceinline__ void obstacle_sum2(const float2 *__restrict__ obs, int M, float c_obs, f2 px,
-                                              f2 py, f2 &sx, f2 &sy) {
+                                              f2 py, f2 &sx, f2 &sy, int first = 0, int stride = 1) {
   f2 ax = bc2(0.f), ay = bc2(0.f);
   const f2 qx = mul2(px, bc2(c_obs)), qy = mul2(py, bc2(c_obs));
-  for (int o = 0; o < M; o += SFW_OBST_CLUSTER_SLOTS) {
+  for (int o = first * SFW_OBST_CLUSTER_SLOTS; o < M; o += stride * SFW_OBST_CLUSTER_SLOTS) {
     const float4 hd = *reinterpret_cast<const float4 *>(obs + o);
     const f2 cx = sub2(qx, bc2(hd.x)), cy = sub2(qy, bc2(hd.y));
     float c0, c1;
