@@ -46,12 +46,19 @@ for ln in lines:
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+\S", ln):
         insts.append((list(chain), ln.strip()))
         fresh = True
-rows = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True,
+# a report with several kernels: NCU_FILTER="--launch-skip 1 --launch-count 1" picks the launch
+rows = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] +
+                                      os.environ.get("NCU_FILTER", "").split(), capture_output=True,
                                       text=True).stdout.splitlines()))
 h = next(i for i, r in enumerate(rows) if "Source" in r and "Address" in r)
 hdr = rows[h]
 ix = {n: k for k, n in enumerate(hdr)}
-sass = [r for r in rows[h + 1:] if len(r) >= len(hdr)]
+sass = []
+for r in rows[h + 1:]:
+    if "Source" in r and "Address" in r:  # newer ncu prints the table once per view: keep the first
+        break
+    if len(r) >= len(hdr):
+        sass.append(r)
 assert len(sass) == len(insts), (len(sass), len(insts))
 
 
