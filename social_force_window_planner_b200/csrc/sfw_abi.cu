@@ -131,18 +131,21 @@ int make_plan(sfw_ctx *c, uint32_t n_scenes, uint32_t samples, uint32_t P, uint3
   if (family == 1 || (family < 0 && c->policy == SFW_POLICY_LATENCY))
     try_small = false;
   const size_t crowd_smem = sfw_crowd_smem_bytes(P, M, F, (uint32_t)steps);
-  if (try_small && family < 0 && c->policy == SFW_POLICY_AUTO && P >= 1 && crowd_smem <= max_dyn) {
+  if (try_small && family < 0 && c->policy == SFW_POLICY_AUTO && crowd_smem <= max_dyn) {
     // Small grids are latency bound in the thread-per-trajectory kernel: one thread walks every pair of a
-    // trajectory, so a tick costs what ONE warp costs (0.9 ms for 20 pedestrians / 40 steps) however few
-    // trajectories there are.  The block-per-trajectory kernel spreads a trajectory's pairs over threads and
-    // runs one block per trajectory: a wave of it takes steps x ~(1 + 0.06 P) us.  Measured crossover
-    // (scripts/latency_probe.py): it wins while its wave count stays below ~0.3 P.
+    // trajectory, so a tick costs what ONE warp costs however few trajectories there are.  The block-per-trajectory
+    // kernel spreads a trajectory's pairs (and obstacle clusters) over threads and runs one block per trajectory.
+    // Measured per rollout step, end to end through sfw_score (scripts/latency_policy_probe.py, latency_probe.py;
+    // 0 ... 40 pedestrians): thread per trajectory 2.1 + 0.63 P + 0.016 P^2 us, block per trajectory
+    // 1.65 + 0.085 P us per WAVE of blocks.  A single wave always wins (116 vs 135 us without pedestrians,
+    // 132 vs 188 us with one, 40 steps); two waves from 3 pedestrians on; at 20 pedestrians up to 6 waves.
     int k = 0;
     CK(c, sfw_crowd_prepare(crowd_smem, &k));
     if (k > 0) {
       const uint64_t total = (uint64_t)n_scenes * samples;
       const uint64_t waves = (total + (uint64_t)c->sm_count * k - 1) / ((uint64_t)c->sm_count * k);
-      if ((double)waves <= 0.3 * (double)P)
+      const double Pd = (double)P;
+      if ((double)waves * (1.65 + 0.085 * Pd) < 2.1 + 0.63 * Pd + 0.016 * Pd * Pd)
         try_small = false;
     }
   }

@@ -453,6 +453,12 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
         un2(fma2(OS, oy, mk2(own.z, own.w)), y0, y1);
         myrow[help_pair] = make_float4(x0, x1, y0, y1);
       }
+      if (tid == kCrowdThreads - 1) { // the robot's obstacle force (never cut off): off the critical path of phase 2
+        float rox, roy;
+        obstacle_sum1(sm.obs, (int)M, B.c_obs, prx, pry, rox, roy);
+        sm.red[3] = rox * a_obs_scale;
+        sm.red[7] = roy * a_obs_scale;
+      }
       {
         float l, h;
         un2(rfx2, l, h);
@@ -535,10 +541,7 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
         rfy = warp_sum(rfy);
         wp = warp_sum(wp);
         if (lane == 0) {
-          float rox, roy;
-          obstacle_sum1(sm.obs, (int)M, B.c_obs, prx, pry, rox, roy);
-          rox *= a_obs_scale;
-          roy *= a_obs_scale;
+          const float rox = sm.red[3], roy = sm.red[7]; // summed by the last thread during phase 1
           const float wr = sqrt_approx(fmaf(rfx, rfx, rfy * rfy)) + sqrt_approx(fmaf(rox, rox, roy * roy));
           social_work += (double)(wr + ((i > 0) ? wp : 0.f));
         }
