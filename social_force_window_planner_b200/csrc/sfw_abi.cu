@@ -138,14 +138,17 @@ int make_plan(sfw_ctx *c, uint32_t n_scenes, uint32_t samples, uint32_t P, uint3
     // Measured per rollout step, end to end through sfw_score (scripts/latency_policy_probe.py, latency_probe.py;
     // 0 ... 40 pedestrians): thread per trajectory 2.1 + 0.63 P + 0.016 P^2 us, block per trajectory
     // 1.65 + 0.085 P us per WAVE of blocks.  A single wave always wins (116 vs 135 us without pedestrians,
-    // 132 vs 188 us with one, 40 steps); two waves from 3 pedestrians on; at 20 pedestrians up to 6 waves.
+    // 132 vs 188 us with one, 40 steps); two waves from 3 pedestrians on; at 20 pedestrians up to 8 waves.
     int k = 0;
     CK(c, sfw_crowd_prepare(crowd_smem, &k));
     if (k > 0) {
       const uint64_t total = (uint64_t)n_scenes * samples;
       const uint64_t waves = (total + (uint64_t)c->sm_count * k - 1) / ((uint64_t)c->sm_count * k);
       const double Pd = (double)P;
-      if ((double)waves * (1.65 + 0.085 * Pd) < 2.1 + 0.63 * Pd + 0.016 * Pd * Pd)
+      // (from 4 pedestrian pairs on the block-per-trajectory kernel spreads its force phase over all warps:
+      // 2.0 + 0.027 P us per step and wave, 155 us end to end at 20 pedestrians, 170 us at 40)
+      const double wave_us = P >= 7 ? 2.0 + 0.027 * Pd : 1.65 + 0.085 * Pd;
+      if ((double)waves * wave_us < 2.1 + 0.63 * Pd + 0.016 * Pd * Pd)
         try_small = false;
     }
   }

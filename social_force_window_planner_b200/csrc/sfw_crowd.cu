@@ -318,7 +318,17 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
     // instead of after them (a tick at the reference's 5 x 9 samples is one wave of this kernel: latency is all
     // there is).  The split only depends on the crowd size, never on the batch or on prefix sharing.
     const uint32_t pair_warps = (P2 + 31u) >> 5;
-    const uint32_t n_help = (P2 && 2u * pair_warps <= (uint32_t)kCrowdWarps) ? (uint32_t)kCrowdWarps / pair_warps - 1u : 0u;
+    // Up to 32 pairs (64 pedestrians: every crowd AUTO sends here for a small grid) one warp would own every pair
+    // and walk its cyclic offsets one after the other.  Instead the force phase is SPREAD over the block: lane a of
+    // every warp stands for pair a; warp 0 takes the robot-pair and the inside-pair forces, warp w = 1 .. 6 the cyclic
+    // offsets w, w + 6, ... (all pairs at once) and the obstacle clusters 6 - w, 12 - w, ... (so the warps with the
+    // fewest offsets get the clusters); the last warp is left to the robot's obstacle sum.  Every warp adds into its
+    // own accumulator row, the rows are summed in warp order after the barrier.  A step then costs about two
+    // pair-force latencies instead of 2 + (P2 - 1) / 2 of them.  (A separate body on purpose: folding the two
+    // layouts into one loop with run-time strides cost the dense-crowd path 5 %.)
+    constexpr uint32_t kSpreadWarps = (uint32_t)kCrowdWarps - 1u; // warps 0 .. 6 share the pedestrians' forces
+    const bool spread = P2 >= 4u && P2 <= 32u; // up to 3 pairs the owner layout with obstacle helpers measured as fast or faster
+    const uint32_t n_help = (!spread && P2 && 2u * pair_warps <= (uint32_t)kCrowdWarps) ? (uint32_t)kCrowdWarps / pair_warps - 1u : 0u;
     const uint32_t help_idx = n_help ? tid / (32u * pair_warps) : 0u; // 0: the threads that own the pairs
     const uint32_t help_pair = n_help ? tid - help_idx * 32u * pair_warps : 0u;
     int steps_done = 0;
@@ -368,6 +378,86 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
         __syncwarp();
       }
       // -- phase 1: forces (sfw_planner.cpp:592) --
+      if (spread) {
+        const uint32_t a = lane;
+        const bool act = a < P2;
+        float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), va = pa;
+        if (act) {
+          pa = sm.pos[a];
+          va = sm.vel[a];
+        }
+        f2 FX = bc2(0.f), FY = bc2(0.f);
+        if (warp == 0u) {
+          if (act) {
+            f2 fx, fy, fm;
+            pair_force2<true>(K, mk2(pa.x, pa.y), mk2(pa.z, pa.w), mk2(va.x, va.y), mk2(va.z, va.w), RX, RY, RVX,
+                              RVY, fx, fy, fm);
+            FX = fx;
+            FY = fy;
+            rfx2 = sub2(rfx2, fx);
+            rfy2 = sub2(rfy2, fy);
+            wp2 = add2(wp2, fm);
+            float gx_, gy_, gm_;
+            pair_force<false>(K, pa.x, pa.z, va.x, va.z, pa.y, pa.w, va.y, va.w, gx_, gy_, gm_);
+            FX = add2(FX, mk2(gx_, -gx_));
+            FY = add2(FY, mk2(gy_, -gy_));
+          }
+        } else if (warp < kSpreadWarps) {
+          const f2 A0X = bc2(pa.x), A0Y = bc2(pa.z), A0VX = bc2(va.x), A0VY = bc2(va.z);
+          const f2 A1X = bc2(pa.y), A1Y = bc2(pa.w), A1VX = bc2(va.y), A1VY = bc2(va.w);
+          f2 s0x = bc2(0.f), s0y = bc2(0.f), s1x = bc2(0.f), s1y = bc2(0.f);
+          const uint32_t n_off = half + (even ? 1u : 0u);
+          for (uint32_t off = warp; off <= n_off; off += kSpreadWarps - 1u) {
+            const bool go = act && (off <= half || a < P2 / 2u);
+            if (go) {
+              uint32_t j = a + off;
+              if (j >= P2)
+                j -= P2;
+              const float4 pb = sm.pos[j], vb = sm.vel[j];
+              const f2 BX = mk2(pb.x, pb.y), BY = mk2(pb.z, pb.w);
+              const f2 BVX = mk2(vb.x, vb.y), BVY = mk2(vb.z, vb.w);
+              f2 hx, hy, gx2, gy2, hm;
+              pair_force2<false>(K, A0X, A0Y, A0VX, A0VY, BX, BY, BVX, BVY, hx, hy, hm);
+              pair_force2<false>(K, A1X, A1Y, A1VX, A1VY, BX, BY, BVX, BVY, gx2, gy2, hm);
+              s0x = add2(s0x, hx);
+              s0y = add2(s0y, hy);
+              s1x = add2(s1x, gx2);
+              s1y = add2(s1y, gy2);
+              const float4 fb4 = myrow[j]; // within one offset the lanes hit distinct entries
+              float bx0, bx1, by0, by1;
+              un2(sub2(mk2(fb4.x, fb4.y), add2(hx, gx2)), bx0, bx1);
+              un2(sub2(mk2(fb4.z, fb4.w), add2(hy, gy2)), by0, by1);
+              myrow[j] = make_float4(bx0, bx1, by0, by1);
+            }
+            __syncwarp();
+          }
+          if (act) {
+            float l0, h0, l1, h1;
+            un2(s0x, l0, h0);
+            un2(s1x, l1, h1);
+            FX = mk2(l0 + h0, l1 + h1);
+            un2(s0y, l0, h0);
+            un2(s1y, l1, h1);
+            FY = mk2(l0 + h0, l1 + h1);
+            if (M) {
+              f2 ox, oy;
+              obstacle_sum2(sm.obs, (int)M, B.c_obs, mk2(pa.x, pa.y), mk2(pa.z, pa.w), ox, oy,
+                            (int)kSpreadWarps - 1 - (int)warp, (int)kSpreadWarps - 1);
+              const float4 Pc = sm.par2[a];
+              const f2 OS = mk2(Pc.x, Pc.y);
+              FX = fma2(OS, ox, FX);
+              FY = fma2(OS, oy, FY);
+            }
+          }
+        }
+        if (act && warp < kSpreadWarps) {
+          const float4 own = myrow[a];
+          float x0, x1, y0, y1;
+          un2(add2(mk2(own.x, own.y), FX), x0, x1);
+          un2(add2(mk2(own.z, own.w), FY), y0, y1);
+          myrow[a] = make_float4(x0, x1, y0, y1);
+        }
+      } else
       for (uint32_t m = 0; m < owned; ++m) {
         const uint32_t a = tid + m * kCrowdThreads;
         const bool act = a < P2;
