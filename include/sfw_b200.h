@@ -217,6 +217,15 @@ int sfw_set_prefix_sharing(sfw_ctx *ctx, int on);
  * always sums every point. */
 int sfw_set_obstacle_cutoff(sfw_ctx *ctx, double cutoff_log2);
 
+/* The obstacle layout sfw_upload builds for one scene, computed on the host (no context, no GPU): the points
+ * scaled by log2(e)/sigma relative to (ref_x, ref_y) and grouped into clusters of 8 behind a 2-slot header
+ * {centre x, centre y}, {reach^2, 0} — 10 float2 slots per cluster, ceil(n / 8) clusters, the last one padded with
+ * points 1e15 away.  r_max = largest agent radius of the scene (metres).  For tests, and for integrators who want
+ * to see what the cutoff will skip.  Returns the number of float2 slots; writes min(slots, slots_cap) of them
+ * (2 floats each) to slots_out (may be NULL to only query the count). */
+uint32_t sfw_obstacle_layout(const double *obstacles_xy, uint32_t n, double ref_x, double ref_y, double sigma,
+                             double r_max, double cutoff_log2, float *slots_out, uint32_t slots_cap);
+
 /* Restrict the next sfw_run calls to linvel rows [row_begin, row_end) of every staged scene
  * (multi-GPU sharding of a single scene across ranks: each rank scores a slab and the winners
  * are all-gathered by the caller).  Rows outside the slab get SFW_COST_SKIPPED. */

@@ -21,7 +21,7 @@ EXPORTS = [
     "sfw_device_costs", "sfw_device_best", "sfw_kernel_launches", "sfw_algorithmic_bytes",
     "sfw_last_kernel", "sfw_shared_prefix_steps", "sfw_h2d_bytes", "sfw_d2h_bytes", "sfw_laser_obstacles", "sfw_marker_points", "sfw_exchange_export", "sfw_exchange_connect",
     "sfw_exchange_sync", "sfw_exchange_fetch", "sfw_exchange_device_buffer", "sfw_set_policy", "sfw_set_prefix_sharing", "sfw_may_i_stop",
-    "sfw_set_obstacle_cutoff", "sfw_obstacle_skip_fraction",
+    "sfw_set_obstacle_cutoff", "sfw_obstacle_skip_fraction", "sfw_obstacle_layout",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -106,6 +106,8 @@ def load() -> C.CDLL:
     lib.sfw_shared_prefix_steps.argtypes = [_ctx]
     lib.sfw_set_obstacle_cutoff.restype = C.c_int
     lib.sfw_set_obstacle_cutoff.argtypes = [_ctx, C.c_double]
+    lib.sfw_obstacle_layout.restype = C.c_uint32
+    lib.sfw_obstacle_layout.argtypes = [_dp, C.c_uint32] + [C.c_double] * 5 + [_fp, C.c_uint32]
     lib.sfw_obstacle_skip_fraction.restype = C.c_double
     lib.sfw_obstacle_skip_fraction.argtypes = [_ctx]
     return lib

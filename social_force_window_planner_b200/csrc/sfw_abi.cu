@@ -1177,6 +1177,21 @@ int sfw_set_obstacle_cutoff(sfw_ctx *c, double cutoff_log2) {
   return SFW_OK;
 }
 
+uint32_t sfw_obstacle_layout(const double *obstacles_xy, uint32_t n, double ref_x, double ref_y, double sigma,
+                             double r_max, double cutoff_log2, float *slots_out, uint32_t slots_cap) {
+  const uint32_t slots = sfw_obst_slots(n);
+  if (!n || !obstacles_xy || !slots_out || !(sigma > 0.0))
+    return (obstacles_xy && sigma > 0.0) ? slots : 0u;
+  const double c_obs_d = (double)(float)(1.4426950408889634 / sigma); // as sfw_upload
+  std::vector<float2> pts(n), rec(slots);
+  for (uint32_t k = 0; k < n; ++k)
+    pts[k] = make_float2((float)((obstacles_xy[2 * k] - ref_x) * c_obs_d),
+                         (float)((obstacles_xy[2 * k + 1] - ref_y) * c_obs_d));
+  pack_obstacles(pts, rec.data(), cutoff_log2, (double)(float)r_max * c_obs_d);
+  memcpy(slots_out, rec.data(), sizeof(float2) * std::min(slots, slots_cap));
+  return slots;
+}
+
 int sfw_set_prefix_sharing(sfw_ctx *c, int on) {
   if (!c)
     return SFW_ERR_ARG;
