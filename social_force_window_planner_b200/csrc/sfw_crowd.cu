@@ -36,6 +36,33 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// The robot's obstacle sum (never cut off) by one whole warp: lane l takes the point pairs l, l + 32, ... of the
+// clustered list (4 pairs per cluster behind its 2-slot header), then a butterfly sum.  All 32 lanes must call.
+__device__ __forceinline__ void robot_obstacle_sum_warp(const float2 *__restrict__ obs, uint32_t M, float c_obs,
+                                                        float px, float py, uint32_t lane, float &sx, float &sy) {
+  f2 ax = bc2(0.f), ay = bc2(0.f);
+  const f2 eps = bc2(1e-30f);
+  const f2 qx = bc2(px * c_obs), qy = bc2(py * c_obs);
+  const uint32_t n4 = (M / SFW_OBST_CLUSTER_SLOTS) * (SFW_OBST_CLUSTER / 2);
+  for (uint32_t i = lane; i < n4; i += 32u) {
+    const uint32_t g = i / (SFW_OBST_CLUSTER / 2), r = i - g * (SFW_OBST_CLUSTER / 2);
+    const float4 p = *reinterpret_cast<const float4 *>(obs + g * SFW_OBST_CLUSTER_SLOTS + 2u + 2u * r);
+    const f2 dx = sub2(qx, mk2(p.x, p.z)), dy = sub2(qy, mk2(p.y, p.w));
+    const f2 d2 = fma2(dx, dx, fma2(dy, dy, eps));
+    const f2 rd = rsqrt2(d2);
+    float d0, d1;
+    un2(mul2(d2, rd), d0, d1);
+    const f2 e = mul2(mk2(ex2_approx(-d0), ex2_approx(-d1)), rd);
+    ax = fma2(e, dx, ax);
+    ay = fma2(e, dy, ay);
+  }
+  float x0, x1, y0, y1;
+  un2(ax, x0, x1);
+  un2(ay, y0, y1);
+  sx = warp_sum(x0 + x1);
+  sy = warp_sum(y0 + y1);
+}
+
 struct CrowdSmem {
   float4 *pos, *vel, *goal, *par, *par2; // [P2]
   float4 *frc;                           // [kCrowdWarps][P2]
@@ -543,11 +570,14 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
         un2(fma2(OS, oy, mk2(own.z, own.w)), y0, y1);
         myrow[help_pair] = make_float4(x0, x1, y0, y1);
       }
-      if (tid == kCrowdThreads - 1) { // the robot's obstacle force (never cut off): off the critical path of phase 2
+      if (warp == (uint32_t)kCrowdWarps - 1u) { // the robot's obstacle force: off the critical path of phase 2
+        __syncwarp();
         float rox, roy;
-        obstacle_sum1(sm.obs, (int)M, B.c_obs, prx, pry, rox, roy);
-        sm.red[3] = rox * a_obs_scale;
-        sm.red[7] = roy * a_obs_scale;
+        robot_obstacle_sum_warp(sm.obs, M, B.c_obs, prx, pry, lane, rox, roy);
+        if (lane == 0u) {
+          sm.red[3] = rox * a_obs_scale;
+          sm.red[7] = roy * a_obs_scale;
+        }
       }
       {
         float l, h;
