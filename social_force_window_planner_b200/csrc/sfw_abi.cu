@@ -1040,7 +1040,8 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     return rc;
   // The tile counters must start at 0 (they self-reset after every launch).  Their offset moves with
   // the sample count, so clear them on every upload: 4 bytes per scene on the same stream.
-  CK(c, cudaMemsetAsync(c->out.dev + c->off_cnt, 0, 4 * (size_t)n_scenes, c->stream));
+  // (the work / done counters of the block-per-trajectory kernel, right behind them, re-arm themselves too)
+  CK(c, cudaMemsetAsync(c->out.dev + c->off_cnt, 0, c->off_work + 64 - c->off_cnt, c->stream));
   c->out_scenes = n_scenes;
   c->out_samples = samples;
 
@@ -1280,14 +1281,14 @@ int sfw_run(sfw_ctx *c) {
       const uint64_t items = (uint64_t)B.n_scenes * (mode == 1 ? 4u : mode == 2 ? c->share_paths - 4u : c->out_samples);
       CK(c, sfw_launch_crowd(W, wc, (uint32_t)std::min<uint64_t>(items, c->plan.grid), c->plan.smem, c->stream, mode == 3));
     }
-    c->launches += 4;
+    c->launches += sfw_crowd_fuses_argmin(W) ? 3 : 4;
     c->last_kernel = "sfw_score_crowd,share";
   } else if (re > rb && c->plan.crowd) {
     SfwBatchDev W = B;
     W.share.mode = 0;
     CK(c, sfw_launch_crowd(W, reinterpret_cast<unsigned int *>(c->out.dev + c->off_work), c->plan.grid,
                            c->plan.smem, c->stream, true));
-    c->launches += 2; // scorer + arg-min
+    c->launches += sfw_crowd_fuses_argmin(W) ? 1 : 2; // scorer (+ arg-min)
     c->last_kernel = "sfw_score_crowd";
   } else if (re > rb && c->share_active && rb == 0 && re == B.n_v) {
     // rollout prefix sharing: the 4 doubly saturated paths, the 2 (n_v + n_w) singly saturated ones (each

@@ -115,8 +115,74 @@ size_t sfw_crowd_smem_bytes(uint32_t P, uint32_t M, uint32_t F, uint32_t S) {
 }
 
 // ================================================================================================
+// Arg-min of one scene's cost vector with the reference's tie-breaks (sfw_planner.cpp:394-414), by one block
+// of 256 threads.  Called from sfw_argmin_kernel (one block per scene) or, for small batches, from the last block
+// of sfw_score_crowd to finish (the costs then come from other SMs: L2 loads).
+// ================================================================================================
+__device__ __forceinline__ void scene_argmin(const SfwBatchDev &B, uint32_t scene, float *s_c, uint32_t *s_i) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t n_w = B.n_w, n = B.n_v * n_w;
+  const float *costs = B.costs + (size_t)scene * n;
+  float bc = -1.f;
+  uint32_t bi = 0u;
+  for (uint32_t i = B.row_begin * n_w + tid; i < B.row_end * n_w; i += 256u) {
+    const float c = __ldcg(costs + i);
+    if (eligible(c, B.linvels[i / n_w]) && better(c, i, bc, bi, B.linvels, B.angvels, n_w)) {
+      bc = c;
+      bi = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float oc = __shfl_xor_sync(0xffffffffu, bc, o);
+    const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(oc, oi, bc, bi, B.linvels, B.angvels, n_w)) {
+      bc = oc;
+      bi = oi;
+    }
+  }
+  if (lane == 0) {
+    s_c[warp] = bc;
+    s_i[warp] = bi;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    bc = (lane < 8u) ? s_c[lane] : -1.f;
+    bi = (lane < 8u) ? s_i[lane] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float oc = __shfl_xor_sync(0xffffffffu, bc, o);
+      const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(oc, oi, bc, bi, B.linvels, B.angvels, n_w)) {
+        bc = oc;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      SfwBest r;
+      r.valid = (bc >= 0.f) ? 1 : 0;
+      r.index = r.valid ? bi : 0u;
+      r.cost = r.valid ? bc : 0.f;
+      r.reserved0 = 0.f;
+      r.v = r.valid ? B.linvels[bi / n_w] : 0.0;
+      r.w = r.valid ? B.angvels[bi % n_w] : 0.0;
+      B.best[scene] = r;
+      if (B.xchg.enabled)
+        export_best(B.xchg, scene, r);
+    }
+  }
+  __syncthreads(); // s_c / s_i may be reused for the next scene
+}
+
+__global__ void __launch_bounds__(256) sfw_argmin_kernel(const __grid_constant__ SfwBatchDev B) {
+  __shared__ float s_c[8];
+  __shared__ uint32_t s_i[8];
+  scene_argmin(B, blockIdx.x, s_c, s_i);
+}
+
+// ================================================================================================
 __global__ void __launch_bounds__(SFW_CROWD_THREADS, 2)
-sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict__ work_counter) {
+sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict__ work_counter, int fused_argmin) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t n_w = B.n_w;
@@ -759,65 +825,27 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
       B.npts[out] = (uint16_t)npts;
     }
   }
-}
-
-// ================================================================================================
-// Arg-min of one scene's cost vector with the reference's tie-breaks (sfw_planner.cpp:394-414),
-// for the kernels that do not reduce in their own epilogue.  One block per scene.
-// ================================================================================================
-__global__ void __launch_bounds__(256) sfw_argmin_kernel(const __grid_constant__ SfwBatchDev B) {
-  const uint32_t scene = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const uint32_t n_w = B.n_w, n = B.n_v * n_w;
-  const float *__restrict__ costs = B.costs + (size_t)scene * n;
-  __shared__ float s_c[8];
-  __shared__ uint32_t s_i[8];
-  float bc = -1.f;
-  uint32_t bi = 0u;
-  for (uint32_t i = B.row_begin * n_w + tid; i < B.row_end * n_w; i += 256u) {
-    const float c = costs[i];
-    if (eligible(c, B.linvels[i / n_w]) && better(c, i, bc, bi, B.linvels, B.angvels, n_w)) {
-      bc = c;
-      bi = i;
+  // ---- epilogue: the last block to run out of work re-arms the two counters (work_counter[0]: next item,
+  // [1]: blocks done) for the next launch and, for small batches, reduces every scene's winner itself: no memset
+  // before and no arg-min launch after the kernel (a 5 x 9 tick is 40 x 3 us of kernel: two extra stream
+  // operations are 5 % of it).
+  __shared__ int s_last;
+  if (tid == 0) {
+    __threadfence(); // this block's costs before its arrival
+    const unsigned int prev = atomicAdd(work_counter + 1, 1u);
+    s_last = (prev == gridDim.x - 1u) ? 1 : 0;
+    if (s_last) {
+      __threadfence();
+      work_counter[0] = 0u;
+      work_counter[1] = 0u;
     }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float oc = __shfl_xor_sync(0xffffffffu, bc, o);
-    const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (better(oc, oi, bc, bi, B.linvels, B.angvels, n_w)) {
-      bc = oc;
-      bi = oi;
-    }
-  }
-  if (lane == 0) {
-    s_c[warp] = bc;
-    s_i[warp] = bi;
   }
   __syncthreads();
-  if (warp == 0) {
-    bc = (lane < 8u) ? s_c[lane] : -1.f;
-    bi = (lane < 8u) ? s_i[lane] : 0u;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float oc = __shfl_xor_sync(0xffffffffu, bc, o);
-      const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (better(oc, oi, bc, bi, B.linvels, B.angvels, n_w)) {
-        bc = oc;
-        bi = oi;
-      }
-    }
-    if (lane == 0) {
-      SfwBest r;
-      r.valid = (bc >= 0.f) ? 1 : 0;
-      r.index = r.valid ? bi : 0u;
-      r.cost = r.valid ? bc : 0.f;
-      r.reserved0 = 0.f;
-      r.v = r.valid ? B.linvels[bi / n_w] : 0.0;
-      r.w = r.valid ? B.angvels[bi % n_w] : 0.0;
-      B.best[scene] = r;
-      if (B.xchg.enabled)
-        export_best(B.xchg, scene, r);
-    }
+  if (s_last && fused_argmin) {
+    float *s_c = reinterpret_cast<float *>(smem_raw);
+    uint32_t *s_i = reinterpret_cast<uint32_t *>(smem_raw + 64);
+    for (uint32_t scene = 0; scene < B.n_scenes; ++scene)
+      scene_argmin(B, scene, s_c, s_i);
   }
 }
 
@@ -829,14 +857,20 @@ cudaError_t sfw_crowd_prepare(size_t smem_bytes, int *blocks_per_sm) {
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, sfw_score_crowd, kCrowdThreads, smem_bytes);
 }
 
+bool sfw_crowd_fuses_argmin(const SfwBatchDev &B) {
+  const uint64_t values = (uint64_t)B.n_scenes * (B.row_end - B.row_begin) * B.n_w;
+  return values <= 8192u && B.n_scenes <= 64u;
+}
+
+// `work_counter`: two words that are 0 before the first launch (sfw_upload clears them) — the kernel re-arms them.
+// Small batches (sfw_crowd_fuses_argmin: at most 8192 cost values in at most 64 scenes) are reduced by the kernel's last block, larger ones by
+// sfw_argmin_kernel with one block per scene.
 cudaError_t sfw_launch_crowd(const SfwBatchDev &B, unsigned int *work_counter, uint32_t grid, size_t smem_bytes,
                              cudaStream_t stream, bool with_argmin) {
-  cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), stream);
-  if (e != cudaSuccess)
-    return e;
-  sfw_score_crowd<<<grid, kCrowdThreads, smem_bytes, stream>>>(B, work_counter);
-  e = cudaGetLastError();
-  if (e != cudaSuccess || !with_argmin)
+  const bool fused = with_argmin && sfw_crowd_fuses_argmin(B);
+  sfw_score_crowd<<<grid, kCrowdThreads, smem_bytes, stream>>>(B, work_counter, fused ? 1 : 0);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || !with_argmin || fused)
     return e;
   sfw_argmin_kernel<<<B.n_scenes, 256, 0, stream>>>(B);
   return cudaGetLastError();
