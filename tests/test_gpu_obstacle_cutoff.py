@@ -123,3 +123,50 @@ def test_batch_with_different_obstacle_counts(fresh):
         c1, b1 = fresh.score(p, [sc], lin, ang)
         assert np.array_equal(c1[0], costs[i])
         parity.compare(p, sc, lin, ang, costs[i], best[i])
+
+
+# ---- block-per-trajectory kernel: layout boundaries of its force phase -------------------------
+@pytest.mark.parametrize("n_peds", [6, 7, 8, 63, 64, 65, 66, 128, 129, 255, 256, 257, 258])
+def test_crowd_kernel_layout_boundaries(fresh, n_peds):
+    """Owner layout with obstacle helpers (up to 3 pairs, 33 .. 128 pairs), spread layout (4 .. 32 pairs), plain owner
+    layout (more than 128 pairs): crowd sizes either side of every switch, odd and even, against the oracle."""
+    fresh.set_policy(fresh.POLICY_LATENCY)
+    wl = dataclasses.replace(S.WORKLOADS["C2"], n_v=3, n_w=4, steps=10, n_peds=n_peds,
+                             ped_r_max=4.0 if n_peds < 70 else 8.0, ped_sep=0.5)
+    sc = S.make_scene(wl, n_peds, n_obstacles=37)
+    p = wl.params()
+    lin, ang = wl.sample_arrays()
+    costs, best = fresh.score(p, [sc], lin, ang)
+    assert fresh.last_kernel == "sfw_score_crowd"
+    print(n_peds, parity.compare(p, sc, lin, ang, costs[0], best[0], max_near_frac=1.0))
+
+
+@pytest.mark.parametrize("n_scenes", [1, 5, 64, 65, 70])
+def test_crowd_kernel_winner_reduction_paths(fresh, n_scenes):
+    """Small batches are reduced by the scorer's last block, larger ones (more than 64 scenes or 8192 cost values) by
+    the arg-min kernel: same winners as one call per scene, launch after launch (the counters re-arm themselves)."""
+    fresh.set_policy(fresh.POLICY_LATENCY)
+    wl = dataclasses.replace(S.WORKLOADS["C0"], n_v=4, n_w=5, steps=8, n_peds=9)
+    scs = [S.make_scene(wl, 40 + i) for i in range(n_scenes)]
+    p = wl.params()
+    lin, ang = wl.sample_arrays()
+    costs, best = fresh.score(p, scs, lin, ang)
+    for rep in range(3):  # sfw_run again on the staged batch
+        fresh.run()
+        c2, b2 = fresh.download()
+        assert np.array_equal(c2, costs) and np.array_equal(b2, best)
+    for i in (0, n_scenes // 2, n_scenes - 1):
+        c1, b1 = fresh.score(p, [scs[i]], lin, ang)
+        assert np.array_equal(c1[0], costs[i]) and b1[0] == best[i]
+        parity.compare(p, scs[i], lin, ang, costs[i], best[i])
+
+
+def test_crowd_kernel_big_grid_unfused_argmin(fresh):
+    """More than 8192 cost values in one scene: arg-min kernel; winner consistent with the cost vector."""
+    fresh.set_policy(fresh.POLICY_LATENCY)
+    wl = dataclasses.replace(S.WORKLOADS["C0"], n_v=96, n_w=96, steps=6, n_peds=4)
+    sc = S.make_scene(wl, 3)
+    p = wl.params()
+    lin, ang = wl.sample_arrays()
+    costs, best = fresh.score(p, [sc], lin, ang)
+    print(parity.compare(p, sc, lin, ang, costs[0], best[0]))
