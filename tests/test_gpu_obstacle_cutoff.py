@@ -5,7 +5,9 @@ computeForces call at reference src/sfw_planner.cpp:592).  The library stores th
 pedestrian pair skips a cluster whose every term is below 2^-24 of the force factor; pedestrians are packed in the
 order of the clusters they reach.  Checked here: the oracle bar with the cutoff on (default) AND off, how far the
 two cost vectors are from each other, cluster edge cases (counts that are not a multiple of 8, one point, more
-than 64 clusters), and that the packed pedestrian order keeps group tags attached to the right pedestrians."""
+than 64 clusters), and that the packed pedestrian order keeps group tags attached to the right pedestrians.
+Second half: the block-per-trajectory kernel's force-phase layouts (which warp sums which obstacle clusters and pair
+offsets depends on the crowd size) either side of every switch, and its two winner-reduction paths."""
 import dataclasses
 
 import numpy as np
