@@ -28,6 +28,60 @@
 static const SfwSfmParams kDefaultSfm = {2.0, 10.0, 0.2, 2.1, 3.0, 2.0, 1.0, 2.0, 0.35, 2.0, 3.0, 0.5};
 
 /* ------------------------------------------------------------------------------------------ */
+/* branch probe (sfw_oracle.h: SfwOracleProbe): record the decisions taken within a margin of  */
+/* their switching surface, and take listed decisions the other way                            */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  SfwOracleMargins *mg; /* nullable */
+  SfwOracleProbe *pr;   /* nullable */
+  int step;
+} Ctx;
+
+/* the decision this run must take for (kind, step, a, b), or `natural` when it is not listed */
+static int probe_decide(Ctx *cx, int kind, int step, int a, int b, int natural) {
+  const SfwOracleProbe *pr = cx ? cx->pr : NULL;
+  if (!pr)
+    return natural;
+  for (uint32_t i = 0; i < pr->n_flips; ++i) {
+    const SfwOracleEvent *f = &pr->flips[i];
+    if (f->kind == kind && f->step == step && f->a == a && f->b == b)
+      return f->decision;
+  }
+  return natural;
+}
+
+static void probe_record(Ctx *cx, int kind, int step, int a, int b, int decision, double margin, double weight) {
+  SfwOracleProbe *pr = cx ? cx->pr : NULL;
+  if (!pr)
+    return;
+  uint32_t n = pr->n_events < pr->max_events ? pr->n_events : pr->max_events;
+  for (uint32_t i = n; i-- > 0;) { /* both directions of a pair report the same decision once */
+    SfwOracleEvent *e = &pr->events[i];
+    if (e->step + 1 < step)
+      break;
+    if (e->step == step && e->kind == kind && e->a == a && e->b == b) {
+      if (margin < e->margin)
+        e->margin = margin;
+      if (weight > e->weight)
+        e->weight = weight;
+      return;
+    }
+  }
+  if (pr->n_events < pr->max_events) {
+    SfwOracleEvent *e = &pr->events[pr->n_events];
+    e->kind = kind;
+    e->step = step;
+    e->a = a;
+    e->b = b;
+    e->decision = decision;
+    e->reserved0 = 0;
+    e->margin = margin;
+    e->weight = weight;
+  }
+  pr->n_events++;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* costmap access: nav2 Costmap2D::worldToMap / getCost  [external, SURVEY.md App. C]          */
 /* ------------------------------------------------------------------------------------------ */
 
@@ -243,7 +297,7 @@ static void normalized2(double x, double y, double *ox, double *oy) {
 /* App. B-3: force on `a` from `b` */
 static void pair_force(const SfwSfmParams *P, double apx, double apy, double avx, double avy,
                        double bpx, double bpy, double bvx, double bvy, double *fx, double *fy,
-                       double *theta_out, double *mag_out) {
+                       double *theta_out, double *mag_out, int force_sgn) {
   double dx = bpx - apx, dy = bpy - apy;
   double ex, ey;
   normalized2(dx, dy, &ex, &ey);
@@ -258,6 +312,8 @@ static void pair_force(const SfwSfmParams *P, double apx, double apy, double avx
   double a1 = P->n_prime * B * theta, a2 = P->n * B * theta;
   double fv = -exp(-dn / B - a1 * a1);
   int sgn = theta == 0.0 ? 0 : (theta > 0.0 ? 1 : -1);
+  if (force_sgn) /* branch probe: the sign this evaluation must use */
+    sgn = force_sgn;
   double fa = -(double)sgn * exp(-dn / B - a2 * a2);
   /* forceVelocity = fv * idir ; forceAngle = fa * leftNormal(idir) = fa * (-idy, idx) */
   *fx = P->force_factor_social * (fv * idx + fa * (-idy));
@@ -272,7 +328,7 @@ void sfw_oracle_pair_force(const SfwSfmParams *sfm, const double me[4], const do
                            double out_fxy[2], double *theta_out) {
   const SfwSfmParams *P = sfm ? sfm : &kDefaultSfm;
   pair_force(P, me[0], me[1], me[2], me[3], other[0], other[1], other[2], other[3], &out_fxy[0],
-             &out_fxy[1], theta_out, NULL);
+             &out_fxy[1], theta_out, NULL, 0);
 }
 
 /* App. B-2 */
@@ -304,18 +360,24 @@ void sfw_oracle_obstacle_force(const SfwSfmParams *sfm, double px, double py, do
 }
 
 /* App. B-1 */
-static void desired_force(const SfwSfmParams *P, OAgent *a, double *goal_margin) {
+static void desired_force(const SfwSfmParams *P, OAgent *a, int idx, Ctx *cx) {
   a->ddx = 0.0;
   a->ddy = 0.0;
   if (a->has_goal) {
     double dx = a->gx - a->px, dy = a->gy - a->py;
     double n = sqrt(dx * dx + dy * dy);
-    if (goal_margin && !a->teleop) {
+    int away = n > a->gr;
+    if (cx && !a->teleop) {
       double m = fabs(n - a->gr);
-      if (m < *goal_margin)
-        *goal_margin = m;
+      if (cx->mg && m < cx->mg->goal)
+        cx->mg->goal = m;
+      if (cx->pr) { /* the same decision update_position took after the previous step (same positions) */
+        if (m < cx->pr->goal_margin)
+          probe_record(cx, SFW_EV_GOAL, cx->step, idx, 0, !away, m, 0.0);
+        away = !probe_decide(cx, SFW_EV_GOAL, cx->step, idx, 0, !away);
+      }
     }
-    if (n > a->gr) {
+    if (away) {
       normalized2(dx, dy, &a->ddx, &a->ddy);
       a->fdx = P->force_factor_desired * (a->ddx * a->vdes - a->vx) / P->relaxation_time;
       a->fdy = P->force_factor_desired * (a->ddy * a->vdes - a->vy) / P->relaxation_time;
@@ -327,7 +389,7 @@ static void desired_force(const SfwSfmParams *P, OAgent *a, double *goal_margin)
 }
 
 /* App. B-4 (only for groupId >= 0 with >= 2 members) */
-static void group_force(const SfwSfmParams *P, OAgent *ag, int n, int idx, double *contact_margin) {
+static void group_force(const SfwSfmParams *P, OAgent *ag, int n, int idx, Ctx *pc) {
   OAgent *a = &ag[idx];
   a->fgx = 0.0;
   a->fgy = 0.0;
@@ -373,12 +435,19 @@ static void group_force(const SfwSfmParams *P, OAgent *ag, int n, int idx, doubl
     if (i == idx || ag[i].group != a->group)
       continue;
     double dx = a->px - ag[i].px, dy = a->py - ag[i].py;
-    if (contact_margin) { /* the repulsion term switches on at contact: a discontinuity of the model */
+    int touching = sqrt(dx * dx + dy * dy) < a->radius + ag[i].radius;
+    if (pc) { /* the repulsion term switches on at contact: a discontinuity of the model */
       double m = fabs(sqrt(dx * dx + dy * dy) - (a->radius + ag[i].radius));
-      if (m < *contact_margin)
-        *contact_margin = m;
+      if (pc->mg && m < pc->mg->collision)
+        pc->mg->collision = m;
+      if (pc->pr) {
+        int lo = idx < i ? idx : i, hi = idx < i ? i : idx;
+        if (m < pc->pr->collision_margin)
+          probe_record(pc, SFW_EV_GROUP, pc->step, lo, hi, touching, m, sqrt(dx * dx + dy * dy));
+        touching = probe_decide(pc, SFW_EV_GROUP, pc->step, lo, hi, touching);
+      }
     }
-    if (sqrt(dx * dx + dy * dy) < a->radius + ag[i].radius) {
+    if (touching) {
       rpx += dx;
       rpy += dy;
     }
@@ -390,11 +459,20 @@ static void group_force(const SfwSfmParams *P, OAgent *ag, int n, int idx, doubl
 }
 
 /* sfm::SFM.computeForces(std::vector<Agent>&): call site src/sfw_planner.cpp:592 */
+static int theta_sign(double th) { return th == 0.0 ? 0 : (th > 0.0 ? 1 : -1); }
+
+/* |theta| and pi - |theta| are the two places where lightsfm's Angle::sign() flips */
+static double theta_margin(double th) {
+  double a = fabs(th);
+  return a < M_PI - a ? a : M_PI - a;
+}
+
 static void compute_forces(const SfwSfmParams *P, OAgent *ag, int n, const double *obs, uint32_t M,
-                           SfwOracleMargins *mg) {
+                           Ctx *cx) {
+  SfwOracleMargins *mg = cx ? cx->mg : NULL;
   for (int i = 0; i < n; ++i) {
     OAgent *a = &ag[i];
-    desired_force(P, a, mg ? &mg->goal : NULL);
+    desired_force(P, a, i, cx);
     obstacle_force(P, a->px, a->py, a->radius, obs, M, &a->fox, &a->foy);
     a->fsx = 0.0;
     a->fsy = 0.0;
@@ -403,20 +481,32 @@ static void compute_forces(const SfwSfmParams *P, OAgent *ag, int n, const doubl
         continue;
       double fx, fy, th, mag;
       pair_force(P, a->px, a->py, a->vx, a->vy, ag[j].px, ag[j].py, ag[j].vx, ag[j].vy, &fx, &fy,
-                 &th, &mag);
+                 &th, &mag, 0);
+      if (cx && cx->pr) { /* theta(i<-j) == theta(j<-i): one decision per unordered pair and step */
+        int lo = i < j ? i : j, hi = i < j ? j : i, nat = theta_sign(th);
+        if (theta_margin(th) < cx->pr->theta_margin && mag > cx->pr->theta_min_weight)
+          probe_record(cx, SFW_EV_THETA, cx->step, lo, hi, nat, theta_margin(th), mag);
+        if (cx->pr->n_flips) {
+          int want = probe_decide(cx, SFW_EV_THETA, cx->step, lo, hi, nat);
+          if (want != nat)
+            pair_force(P, a->px, a->py, a->vx, a->vy, ag[j].px, ag[j].py, ag[j].vx, ag[j].vy, &fx, &fy,
+                       &th, &mag, want);
+        }
+      }
       a->fsx += fx;
       a->fsy += fy;
       if (mg && mag > 1e-6 && fabs(th) < mg->theta)
         mg->theta = fabs(th);
     }
-    group_force(P, ag, n, i, mg ? &mg->collision : NULL);
+    group_force(P, ag, n, i, cx);
     a->Fx = a->fdx + a->fsx + a->fox + a->fgx;
     a->Fy = a->fdy + a->fsy + a->foy + a->fgy;
   }
 }
 
 /* sfm::SFM.updatePosition(std::vector<Agent>&, dt): call site src/sfw_planner.cpp:594 (App. B-5) */
-static void update_position(OAgent *ag, int n, double dt, SfwOracleMargins *mg) {
+static void update_position(OAgent *ag, int n, double dt, Ctx *cx) {
+  SfwOracleMargins *mg = cx ? cx->mg : NULL;
   for (int i = 0; i < n; ++i) {
     OAgent *a = &ag[i];
     if (a->teleop) {
@@ -444,12 +534,18 @@ static void update_position(OAgent *ag, int n, double dt, SfwOracleMargins *mg) 
     if (a->has_goal) {
       double dx = a->gx - a->px, dy = a->gy - a->py;
       double dn = sqrt(dx * dx + dy * dy);
-      if (mg && !a->teleop) {
+      int reached = dn <= a->gr;
+      if (cx && !a->teleop) {
         double m = fabs(dn - a->gr);
-        if (m < mg->goal)
+        if (mg && m < mg->goal)
           mg->goal = m;
+        if (cx->pr) { /* keyed by the step whose force computation sees it */
+          if (m < cx->pr->goal_margin)
+            probe_record(cx, SFW_EV_GOAL, cx->step + 1, i, 0, reached, m, 0.0);
+          reached = probe_decide(cx, SFW_EV_GOAL, cx->step + 1, i, 0, reached);
+        }
       }
-      if (dn <= a->gr)
+      if (reached)
         a->has_goal = 0; /* pop_front; cyclicGoals is false for every agent of the reference */
     }
   }
@@ -475,12 +571,16 @@ static float normalize_angle_f(float val, float mn, float mx) { /* :399-407, all
 }
 
 /* SFWPlanner::scoreTrajectory, src/sfw_planner.cpp:475-676 (+ computeSocialWork :678-705) */
-double sfw_oracle_score_trajectory(const SfwParams *params, const SfwSfmParams *sfm,
-                                   const SfwScene *scene, double vx_samp, double vy_samp,
-                                   double vtheta_samp, double acc_x, double acc_y, double acc_theta,
-                                   double *pts_xyz, uint32_t max_pts, uint32_t *n_pts,
-                                   SfwOracleMargins *mg) {
+static double score_trajectory(const SfwParams *params, const SfwSfmParams *sfm,
+                               const SfwScene *scene, double vx_samp, double vy_samp,
+                               double vtheta_samp, double acc_x, double acc_y, double acc_theta,
+                               double *pts_xyz, uint32_t max_pts, uint32_t *n_pts,
+                               SfwOracleMargins *mg, SfwOracleProbe *pr) {
   const SfwSfmParams *P = sfm ? sfm : &kDefaultSfm;
+  Ctx ctx = {mg, pr, 0};
+  Ctx *cx = (mg || pr) ? &ctx : NULL;
+  if (pr)
+    pr->n_events = 0;
   const SfwRobot *R = &scene->robot;
   int n = (int)scene->n_peds + 1;
   OAgent stack_agents[64];
@@ -529,8 +629,9 @@ double sfw_oracle_score_trajectory(const SfwParams *params, const SfwSfmParams *
   float rr = params->robot_radius * params->robot_radius; /* float product, cpp:617 */
 
   for (int i = 0; i < num_steps; ++i) { /* cpp:540 */
-    unsigned int cx, cy;
-    if (!world_to_map(scene, x_i, y_i, &cx, &cy, NULL)) /* cpp:545-550 */
+    unsigned int cell_x, cell_y;
+    ctx.step = i;
+    if (!world_to_map(scene, x_i, y_i, &cell_x, &cell_y, NULL)) /* cpp:545-550 */
       goto done;
     double fc = sfw_oracle_footprint_cost(scene, x_i, y_i, theta_i, mg ? &mg->cell : NULL); /* :553 */
     if (fc >= 254.0) /* cpp:555-562 */
@@ -557,10 +658,10 @@ double sfw_oracle_score_trajectory(const SfwParams *params, const SfwSfmParams *
     y_i = ny;
     theta_i = theta_i + vtheta_i * dt;
 
-    compute_forces(P, ag, n, scene->obstacles_xy, scene->n_obstacles, mg); /* cpp:592 */
+    compute_forces(P, ag, n, scene->obstacles_xy, scene->n_obstacles, cx); /* cpp:592 */
     double wr = sqrt(ag[0].fsx * ag[0].fsx + ag[0].fsy * ag[0].fsy) +
                 sqrt(ag[0].fox * ag[0].fox + ag[0].foy * ag[0].foy); /* cpp:681-682 (values of :592) */
-    update_position(ag, n, dt, mg); /* cpp:594 */
+    update_position(ag, n, dt, cx); /* cpp:594 */
 
     /* cpp:600-610: the robot agent is overwritten with the rolled state */
     ag[0].px = x_i;
@@ -578,12 +679,18 @@ double sfw_oracle_score_trajectory(const SfwParams *params, const SfwSfmParams *
     for (int j = 1; j < n; ++j) { /* cpp:613-627 */
       double dx = ag[0].px - ag[j].px, dy = ag[0].py - ag[j].py;
       double d = dx * dx + dy * dy;
-      if (mg) {
+      int hit = d <= (double)rr;
+      if (cx) {
         double m = fabs(sqrt(d) - (double)params->robot_radius);
-        if (m < mg->collision)
+        if (mg && m < mg->collision)
           mg->collision = m;
+        if (pr) {
+          if (m < pr->collision_margin)
+            probe_record(cx, SFW_EV_COLLISION, i, 0, j, hit, m, 0.0);
+          hit = probe_decide(cx, SFW_EV_COLLISION, i, 0, j, hit);
+        }
       }
-      if (d <= (double)rr)
+      if (hit)
         goto done;
     }
 
@@ -593,8 +700,9 @@ double sfw_oracle_score_trajectory(const SfwParams *params, const SfwSfmParams *
       if (ag[j].id == ag[0].id) /* lightsfm (Agent&, vector) overload skips equal ids */
         continue;
       double fx, fy, th, mag;
+      /* |f| does not depend on sign(theta): no branch to probe here */
       pair_force(P, ag[j].px, ag[j].py, ag[j].vx, ag[j].vy, ag[0].px, ag[0].py, ag[0].vx, ag[0].vy,
-                 &fx, &fy, &th, &mag);
+                 &fx, &fy, &th, &mag, 0);
       wp += sqrt(fx * fx + fy * fy);
       if (mg && mag > 1e-6 && fabs(th) < mg->theta)
         mg->theta = fabs(th);
@@ -619,6 +727,23 @@ done:
   if (ag != stack_agents)
     free(ag);
   return result;
+}
+
+double sfw_oracle_score_trajectory(const SfwParams *params, const SfwSfmParams *sfm,
+                                   const SfwScene *scene, double vx_samp, double vy_samp,
+                                   double vtheta_samp, double acc_x, double acc_y, double acc_theta,
+                                   double *pts_xyz, uint32_t max_pts, uint32_t *n_pts,
+                                   SfwOracleMargins *mg) {
+  return score_trajectory(params, sfm, scene, vx_samp, vy_samp, vtheta_samp, acc_x, acc_y, acc_theta, pts_xyz,
+                          max_pts, n_pts, mg, NULL);
+}
+
+double sfw_oracle_score_trajectory_probe(const SfwParams *params, const SfwSfmParams *sfm,
+                                         const SfwScene *scene, double vx_samp, double vy_samp,
+                                         double vtheta_samp, double acc_x, double acc_y, double acc_theta,
+                                         SfwOracleProbe *probe) {
+  return score_trajectory(params, sfm, scene, vx_samp, vy_samp, vtheta_samp, acc_x, acc_y, acc_theta, NULL, 0,
+                          NULL, NULL, probe);
 }
 
 /* best-trajectory bookkeeping of findBestAction, src/sfw_planner.cpp:338-344,394-414,426-468 */
@@ -729,6 +854,72 @@ int sfw_oracle_score_mt(const SfwParams *params, const SfwSfmParams *sfm, const 
     pthread_join(th[t], NULL);
   if (best_out)
     sfw_oracle_argmin(costs_out, linvels, n_v, angvels, n_w, best_out);
+  return SFW_OK;
+}
+
+/* The sample loop over samples [first, first + count) with the branch probe on: per sample the cost and the
+ * decisions taken within the thresholds of `cfg` (cfg->flips are applied to EVERY sample: pass none for a
+ * grid).  Samples farmed over n_threads pthreads. */
+typedef struct {
+  const SfwParams *params;
+  const SfwSfmParams *sfm;
+  const SfwScene *scene;
+  const double *linvels, *angvels;
+  uint32_t n_w, first, count;
+  const SfwOracleProbe *cfg;
+  volatile uint32_t *next;
+  double *costs;
+  SfwOracleEvent *events;
+  uint32_t *n_events;
+} ProbeJob;
+
+static void *probe_worker(void *arg) {
+  ProbeJob *j = (ProbeJob *)arg;
+  for (;;) {
+    uint32_t k = __sync_fetch_and_add(j->next, 1u);
+    if (k >= j->count)
+      break;
+    uint32_t i = j->first + k;
+    double linvel = j->linvels[i / j->n_w], angvel = j->angvels[i % j->n_w];
+    if (linvel == 0.0 && angvel == 0.0) {
+      j->costs[k] = -2.0;
+      j->n_events[k] = 0;
+      continue;
+    }
+    SfwOracleProbe pr = *j->cfg;
+    pr.events = j->events + (size_t)k * j->cfg->max_events;
+    pr.n_events = 0;
+    j->costs[k] = score_trajectory(j->params, j->sfm, j->scene, linvel, 0.0, angvel, j->params->max_trans_acc,
+                                   0.0, j->params->max_rot_acc, NULL, 0, NULL, NULL, &pr);
+    j->n_events[k] = pr.n_events;
+  }
+  return NULL;
+}
+
+int sfw_oracle_score_probe(const SfwParams *params, const SfwSfmParams *sfm, const SfwScene *scene,
+                           const double *linvels, uint32_t n_v, const double *angvels, uint32_t n_w,
+                           uint32_t first, uint32_t count, const SfwOracleProbe *cfg, double *costs_out,
+                           SfwOracleEvent *events_out, uint32_t *n_events_out, int n_threads) {
+  if (!params || !scene || !linvels || !angvels || !costs_out || !cfg || !events_out || !n_events_out)
+    return SFW_ERR_ARG;
+  if ((uint64_t)first + count > (uint64_t)n_v * n_w)
+    return SFW_ERR_ARG;
+  if (n_threads < 1)
+    n_threads = 1;
+  if (n_threads > 256)
+    n_threads = 256;
+  volatile uint32_t next = 0;
+  ProbeJob job = {params, sfm, scene, linvels, angvels, n_w, first, count, cfg, &next, costs_out, events_out,
+                  n_events_out};
+  if (n_threads == 1) {
+    probe_worker(&job);
+    return SFW_OK;
+  }
+  pthread_t th[256];
+  for (int t = 0; t < n_threads; ++t)
+    pthread_create(&th[t], NULL, probe_worker, &job);
+  for (int t = 0; t < n_threads; ++t)
+    pthread_join(th[t], NULL);
   return SFW_OK;
 }
 

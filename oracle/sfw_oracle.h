@@ -32,6 +32,52 @@ typedef struct SfwOracleMargins {
   double cell;      /* min distance (metres) of any rasterised world point to a cell boundary */
 } SfwOracleMargins;
 
+/* Branch probe.  The model is discontinuous at a handful of decisions: a pedestrian's goal pops when it comes
+ * within the goal radius (lightsfm updatePosition / computeDesiredForce), the rollout dies when the robot touches
+ * a pedestrian (reference src/sfw_planner.cpp:613-627), lightsfm's angular interaction term carries
+ * sign(theta) (jumps at theta = 0 and |theta| = pi), group repulsion switches on at contact.  A float evaluator
+ * whose state is a few ulps away may legitimately take such a decision the other way when it is taken within
+ * rounding distance of its switching surface.  The probe (i) records every decision taken within the given
+ * margins and (ii) re-runs a trajectory with listed decisions FORCED to a given value, so that a parity test
+ * can require: GPU cost within 1e-4 of the oracle's cost on the branch the GPU took, validity equal to that
+ * branch's — instead of loosening the tolerance near a discontinuity. */
+#define SFW_EV_GOAL 1      /* a = agent index (1..P), b = 0; step = the step whose force pass sees the decision;
+                              decision 1 = goal reached */
+#define SFW_EV_COLLISION 2 /* a = 0, b = pedestrian agent index; decision 1 = hit (rollout invalid) */
+#define SFW_EV_THETA 3     /* a < b agent indices (0 = robot); decision = sign(theta) used by BOTH directions */
+#define SFW_EV_GROUP 4     /* a < b agent indices; decision 1 = touching (repulsion on) */
+typedef struct SfwOracleEvent {
+  int32_t kind, step, a, b;
+  int32_t decision;
+  int32_t reserved0;
+  double margin; /* distance to the switching surface: metres (goal, collision, group) or radians (theta) */
+  double weight; /* theta: magnitude of the angular force term (the jump is twice that); group: distance */
+} SfwOracleEvent;
+
+typedef struct SfwOracleProbe {
+  double goal_margin, collision_margin, theta_margin; /* record decisions closer than this */
+  double theta_min_weight;                            /* ... theta ones only when the term is at least this big */
+  const SfwOracleEvent *flips; /* decisions to force: (kind, step, a, b) -> decision */
+  uint32_t n_flips;
+  uint32_t max_events;
+  SfwOracleEvent *events; /* out: first max_events recorded decisions, in order of occurrence */
+  uint32_t n_events;      /* out: how many were met (may exceed max_events) */
+  uint32_t reserved0;
+} SfwOracleProbe;
+
+/* scoreTrajectory with the probe on. */
+double sfw_oracle_score_trajectory_probe(const SfwParams *params, const SfwSfmParams *sfm,
+                                         const SfwScene *scene, double vx_samp, double vy_samp,
+                                         double vtheta_samp, double acc_x, double acc_y, double acc_theta,
+                                         SfwOracleProbe *probe);
+
+/* Samples [first, first + count) of the (linvels x angvels) grid with the probe on, farmed over n_threads:
+ * costs_out[count], events_out[count][cfg->max_events], n_events_out[count]. */
+int sfw_oracle_score_probe(const SfwParams *params, const SfwSfmParams *sfm, const SfwScene *scene,
+                           const double *linvels, uint32_t n_v, const double *angvels, uint32_t n_w,
+                           uint32_t first, uint32_t count, const SfwOracleProbe *cfg, double *costs_out,
+                           SfwOracleEvent *events_out, uint32_t *n_events_out, int n_threads);
+
 /* One scoreTrajectory call (reference src/sfw_planner.cpp:475-676).  pts_xyz (nullable) receives
  * the recorded (x,y,theta) points, *n_pts their count.  Returns the cost or -1.0. */
 double sfw_oracle_score_trajectory(const SfwParams *params, const SfwSfmParams *sfm,

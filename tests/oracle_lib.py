@@ -27,6 +27,18 @@ class SfwOracleMargins(C.Structure):
 
 MARGIN_DTYPE = np.dtype([("goal", "f8"), ("collision", "f8"), ("theta", "f8"), ("cell", "f8")])
 
+# oracle/sfw_oracle.h: SfwOracleEvent / SfwOracleProbe (the branch probe)
+EVENT_DTYPE = np.dtype([("kind", "i4"), ("step", "i4"), ("a", "i4"), ("b", "i4"), ("decision", "i4"),
+                        ("reserved0", "i4"), ("margin", "f8"), ("weight", "f8")])
+EV_GOAL, EV_COLLISION, EV_THETA, EV_GROUP = 1, 2, 3, 4
+
+
+class SfwOracleProbe(C.Structure):
+    _fields_ = [("goal_margin", C.c_double), ("collision_margin", C.c_double), ("theta_margin", C.c_double),
+                ("theta_min_weight", C.c_double), ("flips", C.c_void_p), ("n_flips", C.c_uint32),
+                ("max_events", C.c_uint32), ("events", C.c_void_p), ("n_events", C.c_uint32),
+                ("reserved0", C.c_uint32)]
+
 
 def build(ref: bool = True) -> None:
     """(Re)build the checkers with oracle/Makefile (the C oracle always; _ref only where
@@ -63,6 +75,15 @@ def oracle():
         lib.sfw_oracle_score_trajectory.argtypes = [C.POINTER(SfwParams), C.POINTER(SfwSfmParams),
                                                     C.POINTER(SfwScene)] + [C.c_double] * 6 + [
             _dp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(SfwOracleMargins)]
+        lib.sfw_oracle_score_trajectory_probe.restype = C.c_double
+        lib.sfw_oracle_score_trajectory_probe.argtypes = [C.POINTER(SfwParams), C.POINTER(SfwSfmParams),
+                                                          C.POINTER(SfwScene)] + [C.c_double] * 6 + [
+            C.POINTER(SfwOracleProbe)]
+        lib.sfw_oracle_score_probe.restype = C.c_int
+        lib.sfw_oracle_score_probe.argtypes = [C.POINTER(SfwParams), C.POINTER(SfwSfmParams), C.POINTER(SfwScene),
+                                               _dp, C.c_uint32, _dp, C.c_uint32, C.c_uint32, C.c_uint32,
+                                               C.POINTER(SfwOracleProbe), _dp, C.c_void_p,
+                                               C.POINTER(C.c_uint32), C.c_int]
         lib.sfw_oracle_argmin.restype = None
         lib.sfw_oracle_argmin.argtypes = [_dp, _dp, C.c_uint32, _dp, C.c_uint32, C.POINTER(SfwBest)]
         lib.sfw_oracle_footprint_cost.restype = C.c_double
@@ -235,6 +256,50 @@ def oracle_score(params, scene, linvels, angvels, sfm=None, margins=False, threa
                                    C.byref(best), mp)
     assert rc == 0
     return costs, best, mg
+
+
+def _probe_cfg(margins, max_events, flips=None):
+    cfg = SfwOracleProbe()
+    cfg.goal_margin, cfg.collision_margin, cfg.theta_margin, cfg.theta_min_weight = margins
+    cfg.max_events = max_events
+    if flips is not None and len(flips):
+        cfg.flips = flips.ctypes.data
+        cfg.n_flips = len(flips)
+    return cfg
+
+
+def oracle_probe_grid(params, scene, linvels, angvels, margins, sfm=None, first=0, count=None, max_events=32,
+                      threads=None):
+    """Samples [first, first + count) of the grid with the branch probe on (oracle/sfw_oracle.h):
+    (costs float64[count], events EVENT_DTYPE[count, max_events], n_events uint32[count])."""
+    sa = scene if isinstance(scene, SceneArray) else SceneArray([scene])
+    lin, ang = _d(linvels), _d(angvels)
+    if count is None:
+        count = len(lin) * len(ang) - first
+    costs = np.empty(count, dtype=np.float64)
+    events = np.zeros((count, max_events), dtype=EVENT_DTYPE)
+    n_ev = np.zeros(count, dtype=np.uint32)
+    cfg = _probe_cfg(margins, max_events)
+    rc = oracle().sfw_oracle_score_probe(C.byref(params), C.byref(sfm) if sfm is not None else None, sa.ptr(0),
+                                         lin.ctypes.data_as(_dp), len(lin), ang.ctypes.data_as(_dp), len(ang),
+                                         first, count, C.byref(cfg), costs.ctypes.data_as(_dp), events.ctypes.data,
+                                         n_ev.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                         int(threads or os.cpu_count() or 1))
+    assert rc == 0
+    return costs, events, n_ev
+
+
+def oracle_probe_one(params, scene, v, w, margins, flips=None, sfm=None, max_events=32):
+    """One trajectory with listed decisions forced (flips: EVENT_DTYPE array): (cost, events met)."""
+    sa = scene if isinstance(scene, SceneArray) else SceneArray([scene])
+    events = np.zeros(max_events, dtype=EVENT_DTYPE)
+    fl = np.ascontiguousarray(flips, dtype=EVENT_DTYPE) if flips is not None else None
+    cfg = _probe_cfg(margins, max_events, fl)
+    cfg.events = events.ctypes.data
+    c = oracle().sfw_oracle_score_trajectory_probe(C.byref(params), C.byref(sfm) if sfm is not None else None,
+                                                   sa.ptr(0), float(v), 0.0, float(w), params.max_trans_acc, 0.0,
+                                                   params.max_rot_acc, C.byref(cfg))
+    return c, events[:min(cfg.n_events, max_events)].copy()
 
 
 def ref_score(params, scene, linvels, angvels, sfm=None, want_best=True):

@@ -52,7 +52,7 @@ def _random_case(seed):
 def test_random_scene_vs_oracle(scorer, seed):
     wl, p, sc, lin, ang = _random_case(seed)
     costs, best = scorer.score(p, [sc], lin, ang)
-    st = parity.compare(p, sc, lin, ang, costs[0], best[0], max_near_frac=1.0)
+    st = parity.compare(p, sc, lin, ang, costs[0], best[0])
     print(seed, wl.n_peds, "peds", len(sc.obstacles), "obst", wl.steps, "steps", scorer.last_kernel, st)
 
 
@@ -67,7 +67,7 @@ def test_random_scene_latency_policy(seed):
         s2.set_policy(Scorer.POLICY_LATENCY)
         costs, best = s2.score(p, [sc], lin, ang)
         assert s2.last_kernel == "sfw_score_crowd"
-        st = parity.compare(p, sc, lin, ang, costs[0], best[0], max_near_frac=1.0)
+        st = parity.compare(p, sc, lin, ang, costs[0], best[0])
         # and the thread-per-trajectory kernel on the same scene agrees with it (same model, other summation order)
         if wl.n_peds <= 64:
             s2.set_policy(Scorer.POLICY_THROUGHPUT)
@@ -119,7 +119,7 @@ def test_random_grid_with_forced_prefix_sharing(seed):
             assert "share" in k_on and "share" not in s2.last_kernel, (k_on, s2.last_kernel)
             assert np.array_equal(c_on, c_off) and np.array_equal(b_on, b_off), k_on
             if pol == Scorer.POLICY_AUTO:
-                st = parity.compare(p, sc, lin, ang, c_on[0], b_on[0], max_near_frac=1.0)
+                st = parity.compare(p, sc, lin, ang, c_on[0], b_on[0])
     finally:
         s2.close()
     print(seed, wl.n_v, "x", wl.n_w, wl.steps, "steps", n_peds, "peds", k_on, st)

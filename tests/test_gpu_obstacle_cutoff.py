@@ -140,7 +140,7 @@ def test_crowd_kernel_layout_boundaries(fresh, n_peds):
     lin, ang = wl.sample_arrays()
     costs, best = fresh.score(p, [sc], lin, ang)
     assert fresh.last_kernel == "sfw_score_crowd"
-    print(n_peds, parity.compare(p, sc, lin, ang, costs[0], best[0], max_near_frac=1.0))
+    print(n_peds, parity.compare(p, sc, lin, ang, costs[0], best[0]))
 
 
 @pytest.mark.parametrize("n_scenes", [1, 5, 64, 65, 70])
