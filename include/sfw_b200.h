@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SFW_ABI_VERSION 3
+#define SFW_ABI_VERSION 4
 
 /* status codes */
 #define SFW_OK 0
@@ -277,22 +277,41 @@ int sfw_laser_obstacles(sfw_ctx *ctx, const SfwLaserScan *scans, uint32_t n_scan
                         uint32_t *n_points_out);
 
 /* ---- multi-GPU: winner exchange fused into the scorer's epilogue -------------------------------
- * One process per GPU, every rank scoring its own scenes (BASELINE configs[3]); the only cross-rank step is
- * that every rank learns every scene's winner.  After sfw_exchange_connect, each sfw_run stores its SfwBest
- * records directly into every rank's gather buffer over NVLink (peer mappings of cudaIpc handles) from the
- * kernel that reduces them; no collective follows the kernel.
+ * One process per GPU.  After sfw_exchange_connect, each sfw_run stores its SfwBest records directly into every
+ * rank's gather buffer over NVLink (peer mappings of cudaIpc handles) from the kernel that reduces them; no
+ * collective follows the kernel.  Two sharding modes (reference loop being sharded: src/sfw_planner.cpp:345-417):
+ *   scene batch (BASELINE configs[3])   rank q scores its own block of scenes; sfw_exchange_fetch returns all of
+ *                                       them, rank after rank = global scene order of a block partition
+ *   row slabs of one batch (configs[1], every rank stages the SAME scenes and scores its linvel rows
+ *   configs[4] on several GPUs)         (sfw_set_row_slab); sfw_exchange_merge reduces the world slab winners of
+ *                                       every scene on the device with the reference's tie-break order
+ *                                       (:394-414), so every rank holds the full grid's winner
  *   sfw_exchange_export   allocate this rank's gather buffer (max_scenes per rank), write its 64-byte
  *                         cudaIpcMemHandle_t to handle_out; the caller ships the handles to all ranks
- *   sfw_exchange_connect  handles = world x 64 bytes in rank order (own slot ignored); world <= 8;
- *                         every rank must stage the SAME number of scenes per tick from here on
+ *   sfw_exchange_connect  handles = world x 64 bytes in rank order (own slot ignored); world <= 8
+ *   sfw_exchange_connect_local  the same for `world` contexts of ONE process (one per GPU, or several on one
+ *                         GPU): ctxs[r] becomes rank r; peers are reached through direct / peer-enabled pointers
+ *   sfw_exchange_expect   scenes_per_rank[world]: how many scenes each rank stages per tick from now on (they may
+ *                         differ); NULL / never called = every rank stages what this rank stages
+ *   sfw_exchange_set_timeout  bound of the device-side arrival wait (default 10 s)
  *   sfw_exchange_sync     enqueue a device-side wait on the context stream until every rank's records of the
  *                         latest sfw_run have arrived (asynchronous for the host)
- *   sfw_exchange_fetch    sync + copy the gathered records to all_best_out[world][n_scenes] (rank major) */
+ *   sfw_exchange_fetch    wait (as above) + copy the gathered records to all_best_out[sum of scenes_per_rank]
+ *   sfw_exchange_merge    wait + device-side merge of the slab winners; merged_out[n_scenes] (NULL: leave them
+ *                         on the device, sfw_exchange_merged_device, and do not synchronise)
+ * A peer that dies, skips a tick or stages fewer scenes than announced does not hang the others: the wait gives
+ * up after the timeout and fetch / merge return SFW_ERR_STATE naming the rank that did not deliver.  An empty
+ * row slab still delivers (invalid) records. */
 int sfw_exchange_export(sfw_ctx *ctx, uint32_t max_scenes, void *handle_out);
 int sfw_exchange_connect(sfw_ctx *ctx, uint32_t rank, uint32_t world, const void *handles);
+int sfw_exchange_connect_local(sfw_ctx *const *ctxs, uint32_t world);
+int sfw_exchange_expect(sfw_ctx *ctx, const uint32_t *scenes_per_rank);
+int sfw_exchange_set_timeout(sfw_ctx *ctx, double seconds);
 int sfw_exchange_sync(sfw_ctx *ctx);
 int sfw_exchange_fetch(sfw_ctx *ctx, SfwBest *all_best_out);
+int sfw_exchange_merge(sfw_ctx *ctx, SfwBest *merged_out);
 const void *sfw_exchange_device_buffer(sfw_ctx *ctx); /* device [world][max_scenes] SfwBest of the latest run */
+const void *sfw_exchange_merged_device(sfw_ctx *ctx); /* device [max_scenes] SfwBest of the latest merge */
 
 /* ---- introspection (benchmark / interop) ---------------------------------------------------- */
 void *sfw_stream(sfw_ctx *ctx);                 /* cudaStream_t the context launches on */

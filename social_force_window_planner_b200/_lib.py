@@ -20,7 +20,8 @@ EXPORTS = [
     "sfw_download", "sfw_sync", "sfw_set_row_slab", "sfw_trajectory_points", "sfw_stream",
     "sfw_device_costs", "sfw_device_best", "sfw_kernel_launches", "sfw_algorithmic_bytes",
     "sfw_last_kernel", "sfw_shared_prefix_steps", "sfw_h2d_bytes", "sfw_d2h_bytes", "sfw_laser_obstacles", "sfw_marker_points", "sfw_exchange_export", "sfw_exchange_connect",
-    "sfw_exchange_sync", "sfw_exchange_fetch", "sfw_exchange_device_buffer", "sfw_set_policy", "sfw_set_prefix_sharing", "sfw_may_i_stop",
+    "sfw_exchange_sync", "sfw_exchange_fetch", "sfw_exchange_device_buffer", "sfw_exchange_expect", "sfw_exchange_connect_local",
+    "sfw_exchange_set_timeout", "sfw_exchange_merge", "sfw_exchange_merged_device", "sfw_set_policy", "sfw_set_prefix_sharing", "sfw_may_i_stop",
     "sfw_set_obstacle_cutoff", "sfw_obstacle_skip_fraction", "sfw_obstacle_layout",
 ]
 
@@ -100,6 +101,16 @@ def load() -> C.CDLL:
     lib.sfw_exchange_fetch.argtypes = [_ctx, C.POINTER(SfwBest)]
     lib.sfw_exchange_device_buffer.restype = C.c_void_p
     lib.sfw_exchange_device_buffer.argtypes = [_ctx]
+    lib.sfw_exchange_merged_device.restype = C.c_void_p
+    lib.sfw_exchange_merged_device.argtypes = [_ctx]
+    lib.sfw_exchange_connect_local.restype = C.c_int
+    lib.sfw_exchange_connect_local.argtypes = [C.POINTER(_ctx), C.c_uint32]
+    lib.sfw_exchange_expect.restype = C.c_int
+    lib.sfw_exchange_expect.argtypes = [_ctx, C.POINTER(C.c_uint32)]
+    lib.sfw_exchange_set_timeout.restype = C.c_int
+    lib.sfw_exchange_set_timeout.argtypes = [_ctx, C.c_double]
+    lib.sfw_exchange_merge.restype = C.c_int
+    lib.sfw_exchange_merge.argtypes = [_ctx, C.POINTER(SfwBest)]
     lib.sfw_last_kernel.restype = C.c_char_p
     lib.sfw_last_kernel.argtypes = [_ctx]
     lib.sfw_shared_prefix_steps.restype = C.c_double

@@ -393,7 +393,7 @@ int sfw_destroy(sfw_ctx *c) {
     if (a->dev)
       cudaFree(a->dev);
   }
-  for (uint32_t q = 0; q < c->xchg.world && c->xchg.connected; ++q)
+  for (uint32_t q = 0; q < c->xchg.world && c->xchg.connected && !c->xchg.local_peers; ++q)
     if (q != c->xchg.rank && c->xchg.peer[q])
       cudaIpcCloseMemHandle(c->xchg.peer[q]);
   if (c->share_buf)
@@ -402,6 +402,8 @@ int sfw_destroy(sfw_ctx *c) {
     cudaFree(c->xchg.local);
   if (c->xchg.host)
     cudaFreeHost(c->xchg.host);
+  if (c->xchg.status)
+    cudaFreeHost(c->xchg.status);
   if (c->d_points)
     cudaFree(c->d_points);
   if (c->h_points)
@@ -1257,9 +1259,12 @@ int sfw_run(sfw_ctx *c) {
   }
   // fused winner exchange: this launch writes epoch parity `slot` of every rank's gather buffer
   memset(&B.xchg, 0, sizeof(B.xchg));
-  if (c->xchg.connected && re > rb) {
+  if (c->xchg.connected) {
     if (B.n_scenes > c->xchg.max_scenes)
       return fail(c, SFW_ERR_ARG, "%u scenes staged but the exchange buffer holds %u", B.n_scenes, c->xchg.max_scenes);
+    if (c->xchg.counts_set && c->xchg.counts[c->xchg.rank] != B.n_scenes)
+      return fail(c, SFW_ERR_ARG, "%u scenes staged but sfw_exchange_expect announced %u for this rank", B.n_scenes,
+                  c->xchg.counts[c->xchg.rank]);
     for (uint32_t q = 0; q < c->xchg.world; ++q) {
       B.xchg.peer_best[q] = reinterpret_cast<SfwBest *>(c->xchg.peer[q]);
       B.xchg.peer_arrived[q] = reinterpret_cast<unsigned int *>((uint8_t *)c->xchg.peer[q] + c->xchg.off_arrived);
@@ -1270,7 +1275,11 @@ int sfw_run(sfw_ctx *c) {
     B.xchg.enabled = 1;
     B.xchg.slot = (uint32_t)(c->xchg.epoch & 1u);
     c->xchg.epoch += 1;
-    c->xchg.expected += B.n_scenes; // every rank stages the same number of scenes per tick
+    for (uint32_t q = 0; q < c->xchg.world; ++q) { // what every rank delivers this tick (sfw_exchange_expect)
+      const uint32_t cnt = c->xchg.counts_set ? c->xchg.counts[q] : B.n_scenes;
+      c->xchg.last_counts[q] = cnt;
+      c->xchg.expected[q] += cnt;
+    }
   }
   if (re > rb && c->plan.crowd && c->share_active && rb == 0 && re == B.n_v) {
     // rollout prefix sharing, block-per-trajectory flavour: paths, paths, samples (+ arg-min)
@@ -1341,8 +1350,13 @@ int sfw_run(sfw_ctx *c) {
     c->launches += 1;
     c->last_kernel = sfw_small_kernel_name(c->plan.T);
   } else {
-    // empty slab: nothing to score, every scene reports "no valid trajectory"
+    // empty slab: nothing to score, every scene reports "no valid trajectory" — to the peers too, who wait for
+    // this rank's records like for anyone else's
     CK(c, cudaMemsetAsync(B.best, 0, sizeof(SfwBest) * B.n_scenes, c->stream));
+    if (B.xchg.enabled) {
+      CK(c, sfw_launch_export_invalid(B.xchg, B.n_scenes, c->stream));
+      c->launches += 1;
+    }
   }
   c->ran = true;
   return SFW_OK;

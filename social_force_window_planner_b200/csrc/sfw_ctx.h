@@ -61,12 +61,18 @@ struct sfw_ctx {
   // fused multi-GPU winner exchange (csrc/sfw_exchange.cu)
   struct {
     bool exported = false, connected = false;
+    bool local_peers = false; // peers are contexts of this process (sfw_exchange_connect_local): nothing to close
     uint32_t rank = 0, world = 1, max_scenes = 0;
-    uint8_t *local = nullptr; // [2][world_max][max_scenes] SfwBest | arrived[SFW_MAX_RANKS]
-    size_t bytes = 0, off_arrived = 0;
+    uint8_t *local = nullptr; // [2][world_max][max_scenes] SfwBest | arrived[SFW_MAX_RANKS] | merged[max_scenes]
+    size_t bytes = 0, off_arrived = 0, off_merged = 0;
     void *peer[SFW_MAX_RANKS] = {};
     uint64_t epoch = 0;     // launches exported so far
-    uint64_t expected = 0;  // records every rank must have delivered by now
+    uint64_t expected[SFW_MAX_RANKS] = {}; // records rank q must have delivered by now
+    uint32_t counts[SFW_MAX_RANKS] = {};   // sfw_exchange_expect: scenes rank q stages per tick
+    uint32_t last_counts[SFW_MAX_RANKS] = {}; // ... of the latest run
+    bool counts_set = false;               // false: every rank stages what this rank stages
+    double timeout_s = 10.0;               // bound of the device-side arrival wait
+    unsigned int *status = nullptr;        // mapped pinned: 0 ok, 1 + q = rank q did not deliver in time
     uint8_t *host = nullptr; // pinned landing buffer of sfw_exchange_fetch
   } xchg;
   double *d_points = nullptr;

@@ -22,6 +22,7 @@ cudaError_t sfw_crowd_prepare(size_t smem_bytes, int *blocks_per_sm);
 bool sfw_crowd_fuses_argmin(const SfwBatchDev &B); // the scorer's last block reduces the winners itself
 cudaError_t sfw_launch_crowd(const SfwBatchDev &B, unsigned int *work_counter, uint32_t grid, size_t smem_bytes,
                              cudaStream_t stream, bool with_argmin);
+cudaError_t sfw_launch_export_invalid(const SfwExchangeDev &X, uint32_t n_scenes, cudaStream_t stream); // sfw_exchange.cu
 cudaError_t sfw_launch_points(const SfwBatchDev &B, uint32_t scene, uint32_t idx, uint32_t n_points,
                               double *out_xyz, cudaStream_t stream);
 cudaError_t sfw_launch_marker_points(const SfwBatchDev &B, uint32_t scene, uint32_t first, uint32_t stride,

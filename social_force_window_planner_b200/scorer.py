@@ -148,16 +148,62 @@ class Scorer:
         blob = b"".join(handles)
         assert len(blob) == 64 * world
         self._xchg_world = world
+        self._xchg_counts = None
         self._check(self._lib.sfw_exchange_connect(self._ctx, rank, world, C.c_char_p(blob)))
+
+    @staticmethod
+    def exchange_connect_local(scorers):
+        """Connect the given scorers of THIS process as ranks 0 .. len - 1 (``sfw_exchange_connect_local``); each
+        must have called ``exchange_export`` with the same ``max_scenes``."""
+        arr = (C.c_void_p * len(scorers))(*[s._ctx.value for s in scorers])
+        rc = scorers[0]._lib.sfw_exchange_connect_local(arr, len(scorers))
+        for s in scorers:
+            s._xchg_world = len(scorers)
+            s._xchg_counts = None
+        if rc != 0:
+            msgs = [s._lib.sfw_last_error(s._ctx).decode() for s in scorers]
+            raise SfwError(rc, "; ".join(m for m in msgs if m))
 
     def exchange_sync(self):
         """Device-side wait (enqueued on the context stream) for every rank's records of the latest run."""
         self._check(self._lib.sfw_exchange_sync(self._ctx))
 
+    def exchange_expect(self, scenes_per_rank):
+        """How many scenes each rank stages per tick from now on (``sfw_exchange_expect``); None = every rank
+        stages what this rank stages."""
+        if scenes_per_rank is None:
+            self._xchg_counts = None
+            self._check(self._lib.sfw_exchange_expect(self._ctx, None))
+            return
+        cnt = np.ascontiguousarray(scenes_per_rank, dtype=np.uint32)
+        assert len(cnt) == self._xchg_world
+        self._xchg_counts = cnt.copy()
+        self._check(self._lib.sfw_exchange_expect(self._ctx, cnt.ctypes.data_as(C.POINTER(C.c_uint32))))
+
+    def exchange_set_timeout(self, seconds: float):
+        """Bound of the device-side arrival wait; a peer that does not deliver makes fetch / merge raise."""
+        self._check(self._lib.sfw_exchange_set_timeout(self._ctx, float(seconds)))
+
     def exchange_fetch(self):
-        """Gathered winners of the latest run: BEST_DTYPE[world, n_scenes] (rank major)."""
-        out = np.zeros((self._xchg_world, self.n_scenes), dtype=BEST_DTYPE)
+        """Gathered winners of the latest run.  Equal scene counts on every rank: BEST_DTYPE[world, n_scenes]
+        (rank major); after ``exchange_expect`` with differing counts: BEST_DTYPE[sum(counts)], rank after rank."""
+        counts = getattr(self, "_xchg_counts", None)
+        total = int(counts.sum()) if counts is not None else self._xchg_world * self.n_scenes
+        out = np.zeros(total, dtype=BEST_DTYPE)
         self._check(self._lib.sfw_exchange_fetch(self._ctx, out.ctypes.data_as(C.POINTER(SfwBest))))
+        if counts is None or (counts == counts[0]).all():
+            return out.reshape(self._xchg_world, -1)
+        return out
+
+    def exchange_merge(self, sync: bool = True):
+        """Row-slab mode: wait for every rank's slab winners and merge them per scene ON THE DEVICE with the
+        reference's tie-break order (``sfw_exchange_merge``).  Returns BEST_DTYPE[n_scenes], or None when
+        ``sync`` is False (the merged records stay on the device)."""
+        if not sync:
+            self._check(self._lib.sfw_exchange_merge(self._ctx, None))
+            return None
+        out = np.zeros(self.n_scenes, dtype=BEST_DTYPE)
+        self._check(self._lib.sfw_exchange_merge(self._ctx, out.ctypes.data_as(C.POINTER(SfwBest))))
         return out
 
     def may_i_stop(self, scene: int, vl_x, vl_y, va, x, y, th, dt):

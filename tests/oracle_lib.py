@@ -314,3 +314,12 @@ def ref_score(params, scene, linvels, angvels, sfm=None, want_best=True):
                              C.byref(best) if want_best else None)
     assert rc == 0
     return costs, best
+
+
+def oracle_argmin(costs, linvels, angvels) -> SfwBest:
+    """Arg-min of a cost vector under the reference's sequential best-update (sfw_oracle_argmin)."""
+    c64, lin, ang = _d(costs).reshape(-1), _d(linvels), _d(angvels)
+    sb = SfwBest()
+    oracle().sfw_oracle_argmin(c64.ctypes.data_as(_dp), lin.ctypes.data_as(_dp), len(lin), ang.ctypes.data_as(_dp),
+                               len(ang), C.byref(sb))
+    return sb

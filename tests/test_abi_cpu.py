@@ -26,7 +26,7 @@ def test_exports_match_header():
     for name in decl:
         assert hasattr(lib, name), f"libsfw_b200.so does not export {name}"
     assert sorted(_lib.EXPORTS) == decl, "python EXPORTS list and header disagree"
-    assert lib.sfw_abi_version() == 3
+    assert lib.sfw_abi_version() == 4
 
 
 def test_struct_layout_matches_header(tmp_path):
