@@ -200,6 +200,13 @@ int sfw_sync(sfw_ctx *ctx);            /* cudaStreamSynchronize on the context s
 #define SFW_POLICY_LATENCY 2
 int sfw_set_policy(sfw_ctx *ctx, int policy);
 
+/* The (0,0) sample.  The reference skips (linvel, angvel) == (0,0) INSIDE its grid loop only
+ * (src/sfw_planner.cpp:349-352); its single scoreTrajectory calls — rotate in place (:225-245), approach the goal
+ * (:298-330) — always evaluate, whatever the velocities.  score_it = 1 scores the (0,0) sample like any other
+ * (set it for single-sample calls; a rotate-in-place with min_in_place_vel_th == 0 is such a sample); 0 (default)
+ * marks it SFW_COST_SKIPPED.  Applies from the next sfw_upload. */
+int sfw_set_zero_sample(sfw_ctx *ctx, int score_it);
+
 /* Rollout prefix sharing (on by default; applies from the next sfw_upload).  With acceleration limits, samples
  * whose velocity is still ramping at the full +-a*dt per step are identical for their first steps; on dense
  * grids (one wave or many) the library simulates those shared prefixes once and starts every sample from the state of

@@ -357,6 +357,16 @@ int sfw_create(sfw_ctx **out, int device, void *stream, const SfwLimits *limits)
     }
     c->own_stream = true;
   }
+  e = cudaHostAlloc((void **)&c->status, 64, cudaHostAllocMapped);
+  if (e == cudaSuccess)
+    e = cudaEventCreateWithFlags(&c->h2d_done, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    sfw_fail(nullptr, SFW_ERR_CUDA, "sfw_create: %s", cudaGetErrorString(e));
+    sfw_destroy(c);
+    return SFW_ERR_CUDA;
+  }
+  memset(c->status, 0, 64);
+  c->xchg.status = c->status + 1;
   if (limits) {
     size_t in_est = (size_t)limits->max_scenes *
                         (sizeof(SfwSceneDev) + (size_t)limits->max_peds * 48 +
@@ -402,8 +412,10 @@ int sfw_destroy(sfw_ctx *c) {
     cudaFree(c->xchg.local);
   if (c->xchg.host)
     cudaFreeHost(c->xchg.host);
-  if (c->xchg.status)
-    cudaFreeHost(c->xchg.status);
+  if (c->status)
+    cudaFreeHost(c->status);
+  if (c->h2d_done)
+    cudaEventDestroy(c->h2d_done);
   if (c->d_points)
     cudaFree(c->d_points);
   if (c->h_points)
@@ -894,6 +906,9 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     return rc;
 
   // ---- pack ----------------------------------------------------------------------------------
+  // sfw_upload is asynchronous: the previous call's H2D copy may still be reading the pinned staging buffer
+  // (upload(A); run; upload(B) without a sync in between) — wait for that copy, not for the whole stream
+  CK(c, cudaEventSynchronize(c->h2d_done));
   uint8_t *h = c->in.host;
   SfwSceneDev *hs = reinterpret_cast<SfwSceneDev *>(h + o_scenes);
   float4 *hPos = reinterpret_cast<float4 *>(h + o_pos);
@@ -1019,6 +1034,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     }
   }
   CK(c, cudaMemcpyAsync(c->in.dev, c->in.host, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(c, cudaEventRecord(c->h2d_done, c->stream));
   c->in_bytes = in_bytes;
   c->scene_host.assign(hs, hs + n_scenes);
 
@@ -1080,6 +1096,8 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   B.win_wp = win_wp;
   B.win_h = win_h;
   B.num_steps = num_steps;
+  B.score_zero = c->score_zero ? 1u : 0u;
+  B.status = c->status;
   B.dt = dt;
   B.max_vel_x = params->max_vel_x;
   B.acc_x = params->max_trans_acc;
@@ -1167,6 +1185,14 @@ int sfw_set_policy(sfw_ctx *c, int policy) {
     return fail(c, SFW_ERR_ARG, "sfw_set_policy: unknown policy %d", policy);
   c->policy = policy;
   c->plan.valid = false;
+  return SFW_OK;
+}
+
+int sfw_set_zero_sample(sfw_ctx *c, int score_it) {
+  if (!c)
+    return SFW_ERR_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->score_zero = score_it ? 1 : 0;
   return SFW_OK;
 }
 
@@ -1385,6 +1411,12 @@ int sfw_download(sfw_ctx *c, float *costs_out, SfwBest *best_out) {
     CK(c, cudaMemcpyAsync(c->out.host + c->off_costs, c->out.dev + c->off_costs, nc,
                           cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
+  if (c->status[0]) { // a kernel gave up (it says why) instead of trapping the context
+    const unsigned int code = c->status[0];
+    c->status[0] = 0u;
+    return fail(c, SFW_ERR_STATE, "scorer kernel gave up (device status %u: %s); results discarded", code,
+                code == SFW_DEVSTAT_PATH_WAIT ? "a shared-path record it continues from never appeared" : "unknown");
+  }
   if (best_out)
     memcpy(best_out, c->out.host + c->off_best, nb);
   if (costs_out)

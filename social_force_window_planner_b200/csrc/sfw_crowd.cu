@@ -266,7 +266,7 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
     }
     const int n_run = writer ? (int)B.share.kmax : S; // steps this item is asked to reach
     const size_t out = (size_t)scene * B.n_v * n_w + idx;
-    if (!writer && v_s == 0.0 && w_s == 0.0) { // sfw_planner.cpp:349-352
+    if (!writer && !B.score_zero && v_s == 0.0 && w_s == 0.0) { // sfw_planner.cpp:349-352
       if (tid == 0) {
         B.costs[out] = SFW_COST_SKIPPED;
         B.npts[out] = 0;

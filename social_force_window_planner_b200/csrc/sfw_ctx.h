@@ -44,6 +44,9 @@ struct sfw_ctx {
   SfwArena sensor_in, sensor_out; // sfw_laser_obstacles / sfw_marker_points staging
   bool laser_attr_set = false;
   int policy = 0; // SFW_POLICY_*
+  int score_zero = 0; // sfw_set_zero_sample
+  unsigned int *status = nullptr; // mapped pinned [16]: [0] scorer kernels (SFW_DEVSTAT_*), [1] winner exchange
+  cudaEvent_t h2d_done = nullptr; // the staging buffer `in.host` may be overwritten once this has fired
   double obst_cutoff_log2 = SFW_OBST_CUTOFF_LOG2; // sfw_set_obstacle_cutoff; <= 0: off
   double obst_skip_frac = 0.0;                    // of the staged batch, at the start poses
 
@@ -72,7 +75,7 @@ struct sfw_ctx {
     uint32_t last_counts[SFW_MAX_RANKS] = {}; // ... of the latest run
     bool counts_set = false;               // false: every rank stages what this rank stages
     double timeout_s = 10.0;               // bound of the device-side arrival wait
-    unsigned int *status = nullptr;        // mapped pinned: 0 ok, 1 + q = rank q did not deliver in time
+    unsigned int *status = nullptr;        // = ctx status + 1 (mapped pinned): 0 ok, 1 + q = rank q did not deliver in time
     uint8_t *host = nullptr; // pinned landing buffer of sfw_exchange_fetch
   } xchg;
   double *d_points = nullptr;

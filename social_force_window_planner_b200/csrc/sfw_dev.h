@@ -65,6 +65,7 @@ struct SfwBlockBest {
   uint32_t index;
 };
 
+#define SFW_DEVSTAT_PATH_WAIT 1u /* merged path launch: a record this path continues from never appeared */
 #define SFW_MAX_RANKS 8
 // Multi-GPU winner exchange fused into the scorer's epilogue (csrc/sfw_exchange.cu): every rank owns a gather
 // buffer [2 epochs][world][max_scenes] of SfwBest plus one arrival counter per source rank; the block that
@@ -143,7 +144,8 @@ struct SfwBatchDev {
   uint32_t tiles_per_scene;
   uint32_t win_wp, win_h; // staged window box (padded width, rows); 0 => read the map from global
   int32_t num_steps;
-  uint32_t pad0;
+  uint32_t score_zero; // 1: the (0,0) sample is scored like any other (single-sample calls, sfw_set_zero_sample)
+  unsigned int *status; // mapped pinned word [0]: a kernel that has to give up says why (SFW_DEVSTAT_*)
   double dt;
   // ControllerParams on the path
   double max_vel_x, acc_x, acc_th;

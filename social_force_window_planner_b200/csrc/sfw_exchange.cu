@@ -164,8 +164,6 @@ int sfw_exchange_export(sfw_ctx *c, uint32_t max_scenes, void *handle_out) {
   SFW_CK(c, cudaMalloc((void **)&c->xchg.local, c->xchg.bytes));
   SFW_CK(c, cudaMemset(c->xchg.local, 0, c->xchg.bytes));
   SFW_CK(c, cudaMallocHost((void **)&c->xchg.host, (size_t)SFW_MAX_RANKS * max_scenes * sizeof(SfwBest)));
-  SFW_CK(c, cudaHostAlloc((void **)&c->xchg.status, 64, cudaHostAllocMapped));
-  memset(c->xchg.status, 0, 64);
   cudaIpcMemHandle_t h;
   SFW_CK(c, cudaIpcGetMemHandle(&h, c->xchg.local));
   static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");

@@ -69,8 +69,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
+  // try_wait suspends in hardware for a bounded time; back off between tries so that the spinning warps of a
+  // block leave the issue slots to the thread that is still setting the copies up
+  while (!mbar_try_wait(bar, parity))
+    __nanosleep(32);
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -295,7 +295,7 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
     v_s = B.linvels[idx / n_w];
     w_s = B.angvels[idx % n_w];
   }
-  const bool skipped = !writer && in_range && (v_s == 0.0 && w_s == 0.0); // sfw_planner.cpp:349-352
+  const bool skipped = !writer && in_range && !B.score_zero && (v_s == 0.0 && w_s == 0.0); // sfw_planner.cpp:349-352
   bool alive = in_range && !skipped;
 
   // ---- per-thread state: one shared-memory column per thread (conflict-free LDS.128) ------------
@@ -335,8 +335,17 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
       if (seen == B.share.epoch)
         break;
       __nanosleep(256);
-      if (clock64() - t0 > (1ll << 33)) // seconds: the host only merges launches whose blocks are all co-resident
-        __trap();
+      if (clock64() - t0 > (1ll << 33)) { // seconds: the host only merges launches whose blocks are all co-resident
+        // give up WITHOUT killing the context: this path (and what forks from it) is garbage, the host sees the
+        // status word after the stream synchronises and fails the call with SFW_ERR_STATE
+        if ((tid & 31u) == 0u) {
+          atomicExch_system(B.status, SFW_DEVSTAT_PATH_WAIT);
+          __threadfence_system();
+        }
+        in_range = false;
+        ck_in = nullptr;
+        break;
+      }
     }
   }
   if (SHARE && ck_in) { // start from the shared path's record of this thread's fork point
@@ -1011,13 +1020,19 @@ const char *sfw_small_kernel_name(uint32_t T, bool share) { return small_variant
 // Largest dynamic shared memory a block of sfw_score_small may request on the current device
 // (opt-in limit minus the kernel's static shared memory); also opts every variant in.
 cudaError_t sfw_small_max_dynamic_smem(size_t *bytes) {
-  static size_t cached = 0;
+  // function attributes are per device: cache (and opt in) per device, not per process
+  static size_t cached_dev[64] = {};
+  int dev = 0;
+  {
+    const cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 != cudaSuccess)
+      return e0;
+  }
+  size_t scratch = 0;
+  size_t &cached = (dev >= 0 && dev < 64) ? cached_dev[dev] : scratch;
   if (!cached) {
-    int dev = 0, optin = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess)
-      return e;
-    e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    int optin = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess)
       return e;
     size_t dyn = (size_t)optin;

@@ -146,6 +146,8 @@ bool SFWPlanner::score(const float rx, const float ry, const float rt, const flo
   sc.n_footprint = (uint32_t)(fp.size() / 2);
 
   costs.assign((size_t)n_v * n_w, 0.0f);
+  // the reference skips (0,0) in its grid loop only; its single scoreTrajectory calls always evaluate
+  sfw_set_zero_sample(ctx_, (uint64_t)n_v * n_w == 1 ? 1 : 0);
   const int rc = sfw_score(ctx_, &p, nullptr, &sc, lin, n_v, ang, n_w, costs.data(), &best);
   if (rc != SFW_OK) {
     error_ = sfw_last_error(ctx_);

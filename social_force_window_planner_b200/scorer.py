@@ -70,6 +70,11 @@ class Scorer:
         """Kernel selection policy (``sfw_set_policy``): AUTO switches small grids to the low-latency kernel."""
         self._check(self._lib.sfw_set_policy(self._ctx, policy))
 
+    def set_zero_sample(self, score_it: bool):
+        """``sfw_set_zero_sample``: score the (0,0) sample (single scoreTrajectory calls of the reference) instead
+        of skipping it (its grid loop)."""
+        self._check(self._lib.sfw_set_zero_sample(self._ctx, 1 if score_it else 0))
+
     def set_prefix_sharing(self, on):
         """Rollout prefix sharing (``sfw_set_prefix_sharing``); bit-identical results.  False / 0 = never,
         True / 1 = when the library's cost model says it pays, 2 = whenever the batch allows it."""
