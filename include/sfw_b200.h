@@ -200,6 +200,12 @@ int sfw_sync(sfw_ctx *ctx);            /* cudaStreamSynchronize on the context s
 #define SFW_POLICY_LATENCY 2
 int sfw_set_policy(sfw_ctx *ctx, int policy);
 
+/* Host workers.  A batch of scenes (sfw_upload / sfw_score_batch with >= 8 scenes) is packed into the staging
+ * arena by n_threads host threads, one scene per work item, and goes to the device in pieces while the next piece
+ * is being packed; big cost-vector downloads are copied out by the same workers.  A single scene (the control
+ * tick) is always packed on the calling thread.  Default: min(16, cores / visible devices); 1 = no workers. */
+int sfw_set_host_threads(sfw_ctx *ctx, int n_threads);
+
 /* The (0,0) sample.  The reference skips (linvel, angvel) == (0,0) INSIDE its grid loop only
  * (src/sfw_planner.cpp:349-352); its single scoreTrajectory calls — rotate in place (:225-245), approach the goal
  * (:298-330) — always evaluate, whatever the velocities.  score_it = 1 scores the (0,0) sample like any other

@@ -20,7 +20,7 @@ EXPORTS = [
     "sfw_download", "sfw_sync", "sfw_set_row_slab", "sfw_trajectory_points", "sfw_stream",
     "sfw_device_costs", "sfw_device_best", "sfw_kernel_launches", "sfw_algorithmic_bytes",
     "sfw_last_kernel", "sfw_shared_prefix_steps", "sfw_h2d_bytes", "sfw_d2h_bytes", "sfw_laser_obstacles", "sfw_marker_points", "sfw_exchange_export", "sfw_exchange_connect",
-    "sfw_exchange_sync", "sfw_exchange_fetch", "sfw_exchange_device_buffer", "sfw_exchange_expect", "sfw_exchange_connect_local", "sfw_set_zero_sample",
+    "sfw_exchange_sync", "sfw_exchange_fetch", "sfw_exchange_device_buffer", "sfw_exchange_expect", "sfw_exchange_connect_local", "sfw_set_zero_sample", "sfw_set_host_threads",
     "sfw_exchange_set_timeout", "sfw_exchange_merge", "sfw_exchange_merged_device", "sfw_set_policy", "sfw_set_prefix_sharing", "sfw_may_i_stop",
     "sfw_set_obstacle_cutoff", "sfw_obstacle_skip_fraction", "sfw_obstacle_layout",
 ]
@@ -89,6 +89,8 @@ def load() -> C.CDLL:
     lib.sfw_may_i_stop.argtypes = [_ctx, C.c_uint32] + [C.c_double] * 7 + [C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]
     lib.sfw_set_prefix_sharing.restype = C.c_int
     lib.sfw_set_prefix_sharing.argtypes = [_ctx, C.c_int]
+    lib.sfw_set_host_threads.restype = C.c_int
+    lib.sfw_set_host_threads.argtypes = [_ctx, C.c_int]
     lib.sfw_set_zero_sample.restype = C.c_int
     lib.sfw_set_zero_sample.argtypes = [_ctx, C.c_int]
     lib.sfw_set_policy.restype = C.c_int

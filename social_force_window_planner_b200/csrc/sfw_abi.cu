@@ -260,9 +260,10 @@ void split_obstacles(std::vector<uint32_t> &idx, const std::vector<float2> &pts,
   split_obstacles(idx, pts, mid, hi);
 }
 
-void pack_obstacles(const std::vector<float2> &pts, float2 *out, double cutoff_log2, double r_max) {
+void pack_obstacles(const std::vector<float2> &pts, float2 *out, double cutoff_log2, double r_max,
+                    std::vector<uint32_t> &idx) {
   const size_t n = pts.size();
-  std::vector<uint32_t> idx(n);
+  idx.resize(n);
   for (size_t i = 0; i < n; ++i)
     idx[i] = (uint32_t)i;
   split_obstacles(idx, pts, 0, n);
@@ -345,6 +346,11 @@ int sfw_create(sfw_ctx **out, int device, void *stream, const SfwLimits *limits)
   sfw_ctx *c = new sfw_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  {
+    // host workers for batches: a fair share of the cores when one process per GPU runs on every visible device
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    c->host_threads = (int)std::min(16u, std::max(1u, hw / (unsigned)std::max(n, 1)));
+  }
   memset(&c->B, 0, sizeof(c->B));
   memset(&c->tmap, 0, sizeof(c->tmap));
   if (stream) {
@@ -442,10 +448,23 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   const SfwSfmParams &sfm = sfm_in ? *sfm_in : kDefaultSfm;
   c->staged = false;
   c->ran = false;
+  SfwScratch &X = c->scratch;
+  // a batch of scenes is packed by the context's host workers (one scene = one item); a lone scene — the control
+  // tick — stays on the calling thread
+  if (n_scenes >= 8 && c->pool.size() < (unsigned)c->host_threads)
+    c->pool.resize((unsigned)c->host_threads);
+  if (X.w.size() < c->pool.size())
+    X.w.resize(c->pool.size());
 
-  // ---- shape scan ------------------------------------------------------------------------------
+  // ---- shape scan: sizes and per-scene prefix offsets ---------------------------------------------
   uint32_t maxP = 0, maxM = 0, maxF = 0, max_sx = 0, max_sy = 0;
-  uint64_t totP = 0, totM = 0, totF = 0;
+  X.off_pairs.assign(n_scenes + 1, 0u);
+  X.off_obst.assign(n_scenes + 1, 0u);
+  X.off_fp.assign(n_scenes + 1, 0u);
+  X.off_grp.assign(n_scenes + 1, 0u);
+  X.off_ped.assign(n_scenes + 1, 0u);
+  X.grp_cnt.assign(n_scenes, 0u);
+  bool any_groups = false;
   for (uint32_t s = 0; s < n_scenes; ++s) {
     const SfwScene &sc = scenes[s];
     if (!sc.costmap || !sc.size_x || !sc.size_y || !(sc.resolution > 0.0))
@@ -464,127 +483,19 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     maxF = std::max(maxF, sc.n_footprint);
     max_sx = std::max(max_sx, sc.size_x);
     max_sy = std::max(max_sy, sc.size_y);
-    totP += (sc.n_peds + 1) / 2;         // pedestrians are stored as pairs
-    totM += sfw_obst_slots(sc.n_obstacles); // clusters of 8 points behind a 2-slot header (sfw_dev.h)
-    totF += sc.n_footprint;
+    uint32_t tagged = 0;
+    for (uint32_t j = 0; j < sc.n_peds; ++j)
+      tagged += sc.peds[j].group_id >= 0 ? 1u : 0u;
+    any_groups = any_groups || tagged >= 2u;
+    X.off_pairs[s + 1] = X.off_pairs[s] + (sc.n_peds + 1) / 2;         // pedestrians are stored as pairs
+    X.off_obst[s + 1] = X.off_obst[s] + sfw_obst_slots(sc.n_obstacles); // clusters of 8 behind a 2-slot header
+    X.off_fp[s + 1] = X.off_fp[s] + sc.n_footprint;
+    X.off_ped[s + 1] = X.off_ped[s] + sc.n_peds;
+    // group table of a scene: start[0 .. G] + 2 words per member; at most tagged / 2 groups of >= 2 members
+    X.off_grp[s + 1] = X.off_grp[s] + (tagged >= 2u ? tagged / 2u + 1u + 2u * tagged : 0u);
   }
-
-  // ---- obstacle clusters, and the pedestrian order that goes with them -------------------------
-  // Obstacle points are stored as compact clusters a pedestrian PAIR skips when both members are out of reach
-  // (obstacle_sum2).  Pedestrians are therefore packed in the order of the clusters they reach from their start
-  // positions, so that the two members of a pair (and neighbouring pairs: the lanes of the block-per-trajectory
-  // kernel) skip the same clusters.  Any order is a valid one: the social force sums over all others.
-  std::vector<float2> obs_packed(totM);
-  std::vector<uint32_t> ped_order, ped_slot; // packed position -> caller's index, and back (flat over scenes)
-  std::vector<uint32_t> ped_first(n_scenes + 1, 0);
-  uint64_t cull_skipped = 0, cull_tests = 0;
-  {
-    uint64_t totPeds = 0;
-    for (uint32_t s = 0; s < n_scenes; ++s)
-      totPeds += scenes[s].n_peds;
-    ped_order.resize(totPeds);
-    ped_slot.resize(totPeds);
-    const double c_obs_d = (double)(float)(1.4426950408889634 / sfm.force_sigma_obstacle);
-    std::vector<float2> pts;
-    std::vector<uint64_t> reach; // per pedestrian: bit g = cluster g within reach, words_per pedestrian
-    std::vector<uint32_t> reach_n;
-    size_t pM = 0, pJ = 0;
-    for (uint32_t s = 0; s < n_scenes; ++s) {
-      const SfwScene &sc = scenes[s];
-      const SfwRobot &R = sc.robot;
-      ped_first[s] = (uint32_t)pJ;
-      float r_max = (float)R.agent_radius;
-      for (uint32_t j = 0; j < sc.n_peds; ++j)
-        r_max = std::max(r_max, (float)sc.peds[j].radius);
-      pts.resize(sc.n_obstacles);
-      for (uint32_t k = 0; k < sc.n_obstacles; ++k)
-        pts[k] = make_float2((float)((sc.obstacles_xy[2 * k] - R.x) * c_obs_d),
-                             (float)((sc.obstacles_xy[2 * k + 1] - R.y) * c_obs_d));
-      float2 *rec = obs_packed.data() + pM;
-      pack_obstacles(pts, rec, c->obst_cutoff_log2, (double)r_max * c_obs_d);
-      const uint32_t slots = sfw_obst_slots(sc.n_obstacles), n_cl = slots / SFW_OBST_CLUSTER_SLOTS;
-      uint32_t *order = ped_order.data() + pJ;
-      for (uint32_t j = 0; j < sc.n_peds; ++j)
-        order[j] = j;
-      if (c->obst_cutoff_log2 > 0.0 && n_cl && sc.n_peds) {
-        const uint32_t words = (n_cl + 63u) / 64u;
-        reach.assign((size_t)sc.n_peds * words, 0ull);
-        reach_n.assign(sc.n_peds, 0u);
-        for (uint32_t j = 0; j < sc.n_peds; ++j) {
-          const float qx = (float)(sc.peds[j].x - R.x) * (float)c_obs_d, qy = (float)(sc.peds[j].y - R.y) * (float)c_obs_d;
-          for (uint32_t g = 0; g < n_cl; ++g) {
-            const float dx = qx - rec[g * SFW_OBST_CLUSTER_SLOTS].x, dy = qy - rec[g * SFW_OBST_CLUSTER_SLOTS].y;
-            if (dx * dx + dy * dy <= rec[g * SFW_OBST_CLUSTER_SLOTS + 1].x) {
-              reach[(size_t)j * words + g / 64u] |= 1ull << (g & 63u);
-              ++reach_n[j];
-            }
-          }
-        }
-        std::sort(order, order + sc.n_peds, [&](uint32_t a, uint32_t b) {
-          if (reach_n[a] != reach_n[b])
-            return reach_n[a] > reach_n[b];
-          for (uint32_t w = 0; w < words; ++w)
-            if (reach[(size_t)a * words + w] != reach[(size_t)b * words + w])
-              return reach[(size_t)a * words + w] < reach[(size_t)b * words + w];
-          return a < b;
-        });
-        // share of (pair, cluster) tests that skip the cluster at the start positions (reported only)
-        for (uint32_t k = 0; k < sc.n_peds; k += 2) {
-          const uint32_t a = order[k], b = (k + 1 < sc.n_peds) ? order[k + 1] : order[k];
-          for (uint32_t w = 0; w < words; ++w) {
-            const uint64_t either = reach[(size_t)a * words + w] | reach[(size_t)b * words + w];
-            cull_skipped += (w + 1 < words ? 64u : n_cl - 64u * w) - (uint32_t)__builtin_popcountll(either);
-          }
-          cull_tests += n_cl;
-        }
-      }
-      for (uint32_t j = 0; j < sc.n_peds; ++j)
-        ped_slot[pJ + order[j]] = j;
-      pM += slots;
-      pJ += sc.n_peds;
-    }
-    ped_first[n_scenes] = (uint32_t)pJ;
-  }
-
-  // ---- pedestrian groups: lightsfm only applies group forces to groups with >= 2 members ------
-  std::vector<uint32_t> grp_table;
-  std::vector<uint32_t> grp_off(n_scenes), grp_cnt(n_scenes);
-  {
-    std::vector<std::pair<int32_t, uint32_t>> tagged;
-    for (uint32_t s = 0; s < n_scenes; ++s) {
-      const SfwScene &sc = scenes[s];
-      tagged.clear();
-      for (uint32_t j = 0; j < sc.n_peds; ++j)
-        if (sc.peds[j].group_id >= 0)
-          tagged.emplace_back(sc.peds[j].group_id, j);
-      std::stable_sort(tagged.begin(), tagged.end(),
-                       [](const std::pair<int32_t, uint32_t> &a, const std::pair<int32_t, uint32_t> &b) { return a.first < b.first; });
-      std::vector<uint32_t> starts, members;
-      for (size_t i = 0; i < tagged.size();) {
-        size_t e = i;
-        while (e < tagged.size() && tagged[e].first == tagged[i].first)
-          ++e;
-        if (e - i >= 2) {
-          starts.push_back((uint32_t)(members.size() / 2));
-          for (size_t m = i; m < e; ++m) {
-            const float rad = (float)sc.peds[tagged[m].second].radius;
-            uint32_t bits;
-            memcpy(&bits, &rad, 4);
-            members.push_back(ped_slot[ped_first[s] + tagged[m].second]); // index in the packed order
-            members.push_back(bits);
-          }
-        }
-        i = e;
-      }
-      grp_off[s] = (uint32_t)grp_table.size();
-      grp_cnt[s] = (uint32_t)starts.size();
-      if (!starts.empty()) {
-        starts.push_back((uint32_t)(members.size() / 2));
-        grp_table.insert(grp_table.end(), starts.begin(), starts.end());
-        grp_table.insert(grp_table.end(), members.begin(), members.end());
-      }
-    }
-  }
+  const uint64_t totP = X.off_pairs[n_scenes], totM = X.off_obst[n_scenes], totF = X.off_fp[n_scenes];
+  const uint64_t totG = X.off_grp[n_scenes];
 
   // ---- rollout constants --------------------------------------------------------------------
   int num_steps = (int)(params->sim_time / params->sim_granularity + 0.5); // sfw_planner.cpp:519
@@ -599,7 +510,8 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   for (uint32_t i = 0; i < n_v; ++i)
     max_lin = std::max(max_lin, std::fabs(linvels[i]));
   uint32_t win_wp = 0, win_h = 0;
-  std::vector<int32_t> wx0(n_scenes), wy0(n_scenes);
+  X.wx0.assign(n_scenes, 0);
+  X.wy0.assign(n_scenes, 0);
   {
     int64_t need = 0;
     bool ok = true;
@@ -627,8 +539,8 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
       // and widen the box by the slack.
       const int64_t x0 = (int64_t)cxd - rc;
       const int64_t x0a = (x0 >= 0) ? (x0 / 16) * 16 : -(((-x0) + 15) / 16) * 16;
-      wx0[s] = (int32_t)x0a;
-      wy0[s] = (int32_t)((int64_t)cyd - rc);
+      X.wx0[s] = (int32_t)x0a;
+      X.wy0[s] = (int32_t)((int64_t)cyd - rc);
       need = std::max<int64_t>(need, 2 * rc + 1);
     }
     if (ok && need > 0) {
@@ -653,66 +565,78 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   // compare): update k of row r is "saturated" iff the ramp vi +- a*dt does not reach the target yet.
   const bool share_candidate = c->share_allowed && c->policy != SFW_POLICY_LATENCY && (uint64_t)n_v * n_w >= 1024 &&
                                num_steps >= 8;
-  std::vector<uint16_t> sh_kv, sh_kw;
-  std::vector<uint8_t> sh_dv, sh_dw;
-  std::vector<uint32_t> sh_perm, sh_rperm, sh_lvl_rows, sh_lvl_cols, sh_chunk_map;
   uint32_t sh_kmax = 0;
   double sh_mean_s0 = 0.0;
+  X.kv.clear();
+  X.kw.clear();
+  X.dv.clear();
+  X.dw.clear();
+  X.perm.clear();
+  X.rperm.clear();
+  X.lvl_rows.clear();
+  X.lvl_cols.clear();
+  X.chunk_map.clear();
   if (share_candidate) {
     const int kcap = std::min(num_steps - 1, 96);
+    const double ax_dt = params->max_trans_acc * dt, ath_dt = params->max_rot_acc * dt;
+    X.kv.resize((size_t)n_scenes * n_v);
+    X.dv.resize((size_t)n_scenes * n_v);
+    X.kw.resize((size_t)n_scenes * n_w);
+    X.dw.resize((size_t)n_scenes * n_w);
+    for (SfwScratch::Worker &w : X.w) {
+      w.kmax = 0;
+      w.tot = 0.0;
+      w.up.resize(kcap + 1);
+      w.dn.resize(kcap + 1);
+    }
     // the saturated ramps are the same for every row / column of a scene: build them once per scene (the
     // additions are the kernel's own, sequentially rounded), then count how far each target lets them run
-    std::vector<double> up(kcap + 1), dn(kcap + 1);
-    auto build = [&](double v0, double a_dt) {
-      up[0] = dn[0] = v0;
-      for (int k = 1; k <= kcap; ++k) {
-        up[k] = up[k - 1] + a_dt;
-        dn[k] = dn[k - 1] - a_dt;
-      }
-    };
-    auto ramp = [&](double target, double v0, double a_dt, uint16_t &k_out, uint8_t &dir_out) {
-      const bool rising = (target - v0) >= 0.0;
-      int k = 0;
-      if (a_dt > 0.0) {
-        if (rising)
-          while (k < kcap && target >= up[k + 1])
-            ++k;
-        else
-          while (k < kcap && target <= dn[k + 1])
-            ++k;
-      }
-      k_out = (uint16_t)k;
-      dir_out = rising ? 1 : 0;
-    };
-    const double ax_dt = params->max_trans_acc * dt, ath_dt = params->max_rot_acc * dt;
-    sh_kv.resize((size_t)n_scenes * n_v);
-    sh_dv.resize((size_t)n_scenes * n_v);
-    sh_kw.resize((size_t)n_scenes * n_w);
-    sh_dw.resize((size_t)n_scenes * n_w);
-    for (uint32_t s = 0; s < n_scenes; ++s) {
+    c->pool.run(n_scenes, [&](uint32_t s, unsigned wi) {
+      SfwScratch::Worker &W = X.w[wi];
+      std::vector<double> &up = W.up, &dn = W.dn;
+      auto build = [&](double v0, double a_dt) {
+        up[0] = dn[0] = v0;
+        for (int k = 1; k <= kcap; ++k) {
+          up[k] = up[k - 1] + a_dt;
+          dn[k] = dn[k - 1] - a_dt;
+        }
+      };
+      auto ramp = [&](double target, double v0, double a_dt, uint16_t &k_out, uint8_t &dir_out) {
+        const bool rising = (target - v0) >= 0.0;
+        int k = 0;
+        if (a_dt > 0.0) {
+          if (rising)
+            while (k < kcap && target >= up[k + 1])
+              ++k;
+          else
+            while (k < kcap && target <= dn[k + 1])
+              ++k;
+        }
+        k_out = (uint16_t)k;
+        dir_out = rising ? 1 : 0;
+        W.kmax = std::max<uint32_t>(W.kmax, (uint32_t)k);
+      };
       build(scenes[s].robot.vx, ax_dt);
       for (uint32_t r = 0; r < n_v; ++r)
-        ramp(linvels[r], scenes[s].robot.vx, ax_dt, sh_kv[(size_t)s * n_v + r], sh_dv[(size_t)s * n_v + r]);
+        ramp(linvels[r], scenes[s].robot.vx, ax_dt, X.kv[(size_t)s * n_v + r], X.dv[(size_t)s * n_v + r]);
       build(scenes[s].robot.vtheta, ath_dt);
       for (uint32_t q = 0; q < n_w; ++q)
-        ramp(angvels[q], scenes[s].robot.vtheta, ath_dt, sh_kw[(size_t)s * n_w + q], sh_dw[(size_t)s * n_w + q]);
-    }
-    for (uint16_t k : sh_kv)
-      sh_kmax = std::max<uint32_t>(sh_kmax, k);
-    for (uint16_t k : sh_kw)
-      sh_kmax = std::max<uint32_t>(sh_kmax, k);
+        ramp(angvels[q], scenes[s].robot.vtheta, ath_dt, X.kw[(size_t)s * n_w + q], X.dw[(size_t)s * n_w + q]);
+    }, 64);
+    for (const SfwScratch::Worker &w : X.w)
+      sh_kmax = std::max(sh_kmax, w.kmax);
     // per scene: rows sorted by kv, columns by kw (counting sorts), how many fork before each step, and the mean
     // fork step max(kv, kw) over the grid (from the prefix counts)
     const uint32_t L = sh_kmax + 2u;
-    sh_perm.resize((size_t)n_scenes * n_w);
-    sh_rperm.resize((size_t)n_scenes * n_v);
-    sh_lvl_rows.assign((size_t)n_scenes * L, 0u);
-    sh_lvl_cols.assign((size_t)n_scenes * L, 0u);
-    std::vector<uint32_t> cur(L);
-    double tot = 0.0;
-    for (uint32_t s = 0; s < n_scenes; ++s) {
-      const uint16_t *kvs = sh_kv.data() + (size_t)s * n_v, *kws = sh_kw.data() + (size_t)s * n_w;
-      uint32_t *lr = sh_lvl_rows.data() + (size_t)s * L, *lc = sh_lvl_cols.data() + (size_t)s * L;
+    X.perm.resize((size_t)n_scenes * n_w);
+    X.rperm.resize((size_t)n_scenes * n_v);
+    X.lvl_rows.assign((size_t)n_scenes * L, 0u);
+    X.lvl_cols.assign((size_t)n_scenes * L, 0u);
+    c->pool.run(n_scenes, [&](uint32_t s, unsigned wi) {
+      SfwScratch::Worker &W = X.w[wi];
+      W.cur.resize(L);
+      const uint16_t *kvs = X.kv.data() + (size_t)s * n_v, *kws = X.kw.data() + (size_t)s * n_w;
+      uint32_t *lr = X.lvl_rows.data() + (size_t)s * L, *lc = X.lvl_cols.data() + (size_t)s * L;
       for (uint32_t r = 0; r < n_v; ++r)
         ++lr[kvs[r] + 1u];
       for (uint32_t q = 0; q < n_w; ++q)
@@ -722,14 +646,17 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
         lc[k] += lc[k - 1u];
       }
       for (uint32_t k = 1; k <= sh_kmax; ++k) // sum of max(kv, kw) = sum over k >= 1 of #{max >= k}
-        tot += (double)n_v * n_w - (double)lr[k] * (double)lc[k];
-      std::copy(lr, lr + L, cur.begin());
+        W.tot += (double)n_v * n_w - (double)lr[k] * (double)lc[k];
+      std::copy(lr, lr + L, W.cur.begin());
       for (uint32_t r = 0; r < n_v; ++r)
-        sh_rperm[(size_t)s * n_v + cur[kvs[r]]++] = r;
-      std::copy(lc, lc + L, cur.begin());
+        X.rperm[(size_t)s * n_v + W.cur[kvs[r]]++] = r;
+      std::copy(lc, lc + L, W.cur.begin());
       for (uint32_t q = 0; q < n_w; ++q)
-        sh_perm[(size_t)s * n_w + cur[kws[q]]++] = q;
-    }
+        X.perm[(size_t)s * n_w + W.cur[kws[q]]++] = q;
+    }, 64);
+    double tot = 0.0;
+    for (const SfwScratch::Worker &w : X.w)
+      tot += w.tot;
     sh_mean_s0 = tot / ((double)n_scenes * n_v * n_w);
   }
   // ---- worth it?  Sharing removes the first max(kv, kw) steps of every sample and costs two latency-bound
@@ -781,7 +708,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
       auto thread_cost = [&](double blocks) { return sh_kmax * t_thr * std::ceil(blocks / slots) + 20.0; };
       const double paths2 = (double)(share_paths - 4u);
       double c1 = thread_cost((double)n_scenes), c2 = thread_cost((double)n_scenes * std::ceil(paths2 / 128.0));
-      if (grp_table.empty()) {
+      if (!any_groups) {
         const double w1 = warp_cost((double)n_scenes);
         const double w2 = warp_cost((double)n_scenes * std::ceil(paths2 / (SFW_PATH_WARP_THREADS / 32.0)));
         if (w1 < c1) {
@@ -834,7 +761,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
             bins.push_back({(warps - q + 3u) / 4u, b, q});
       }
       std::stable_sort(bins.begin(), bins.end(), [](const Bin &a, const Bin &b) { return a.cap < b.cap; });
-      sh_chunk_map.assign((size_t)nblk * wpb, 0u);
+      X.chunk_map.assign((size_t)nblk * wpb, 0u);
       uint32_t ch = 0; // chunks in ascending fork step = longest first
       for (size_t b0 = 0; b0 < bins.size();) {
         size_t b1 = b0;
@@ -844,7 +771,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
         for (uint32_t slot = 0; slot < bins[b0].cap; ++slot)
           for (size_t i = 0; i < nb; ++i, ++ch) {
             const Bin &bn = bins[b0 + ((slot & 1u) ? nb - 1 - i : i)];
-            sh_chunk_map[(size_t)bn.blk * wpb + bn.sch + 4u * slot] = ch;
+            X.chunk_map[(size_t)bn.blk * wpb + bn.sch + 4u * slot] = ch;
           }
         b0 = b1;
       }
@@ -875,29 +802,29 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   const size_t o_fp = off;
   off = align_up(off + 16 * totF, kAlign);
   const size_t o_grp = off;
-  off = align_up(off + 4 * grp_table.size(), kAlign);
+  off = align_up(off + 4 * totG, kAlign);
   const size_t o_lin = off;
   off = align_up(off + 8 * (size_t)n_v, kAlign);
   const size_t o_ang = off;
   off = align_up(off + 8 * (size_t)n_w, kAlign);
   const size_t o_skv = off;
-  off = align_up(off + 2 * sh_kv.size(), kAlign);
+  off = align_up(off + 2 * X.kv.size(), kAlign);
   const size_t o_skw = off;
-  off = align_up(off + 2 * sh_kw.size(), kAlign);
+  off = align_up(off + 2 * X.kw.size(), kAlign);
   const size_t o_sdv = off;
-  off = align_up(off + sh_dv.size(), kAlign);
+  off = align_up(off + X.dv.size(), kAlign);
   const size_t o_sdw = off;
-  off = align_up(off + sh_dw.size(), kAlign);
+  off = align_up(off + X.dw.size(), kAlign);
   const size_t o_sperm = off;
-  off = align_up(off + 4 * sh_perm.size(), kAlign);
+  off = align_up(off + 4 * X.perm.size(), kAlign);
   const size_t o_srperm = off;
-  off = align_up(off + 4 * sh_rperm.size(), kAlign);
+  off = align_up(off + 4 * X.rperm.size(), kAlign);
   const size_t o_slr = off;
-  off = align_up(off + 4 * sh_lvl_rows.size(), kAlign);
+  off = align_up(off + 4 * X.lvl_rows.size(), kAlign);
   const size_t o_slc = off;
-  off = align_up(off + 4 * sh_lvl_cols.size(), kAlign);
+  off = align_up(off + 4 * X.lvl_cols.size(), kAlign);
   const size_t o_scm = off;
-  off = align_up(off + 4 * sh_chunk_map.size(), kAlign);
+  off = align_up(off + 4 * X.chunk_map.size(), kAlign);
   const size_t o_maps = off;
   off = align_up(off + slot * n_scenes, kAlign);
   const size_t in_bytes = off;
@@ -919,28 +846,121 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   uint8_t *hBits = h + o_gbits;
   float2 *hO = reinterpret_cast<float2 *>(h + o_obs);
   double2 *hF = reinterpret_cast<double2 *>(h + o_fp);
-  if (!grp_table.empty())
-    memcpy(h + o_grp, grp_table.data(), 4 * grp_table.size());
-  if (share_candidate) {
-    memcpy(h + o_skv, sh_kv.data(), 2 * sh_kv.size());
-    memcpy(h + o_skw, sh_kw.data(), 2 * sh_kw.size());
-    memcpy(h + o_sdv, sh_dv.data(), sh_dv.size());
-    memcpy(h + o_sdw, sh_dw.data(), sh_dw.size());
-    memcpy(h + o_sperm, sh_perm.data(), 4 * sh_perm.size());
-    memcpy(h + o_srperm, sh_rperm.data(), 4 * sh_rperm.size());
-    memcpy(h + o_slr, sh_lvl_rows.data(), 4 * sh_lvl_rows.size());
-    memcpy(h + o_slc, sh_lvl_cols.data(), 4 * sh_lvl_cols.size());
-    if (!sh_chunk_map.empty())
-      memcpy(h + o_scm, sh_chunk_map.data(), 4 * sh_chunk_map.size());
-  }
+  uint32_t *hG = reinterpret_cast<uint32_t *>(h + o_grp);
+  if (share_candidate && !X.chunk_map.empty())
+    memcpy(h + o_scm, X.chunk_map.data(), 4 * X.chunk_map.size());
   memcpy(h + o_lin, linvels, 8 * (size_t)n_v);
   memcpy(h + o_ang, angvels, 8 * (size_t)n_w);
-  uint32_t pP = 0, pM = 0, pF = 0;
   const double inv_sigma = 1.0 / sfm.force_sigma_obstacle;
   const double c_obs_d = (double)(float)(1.4426950408889634 * inv_sigma); // the float the kernel multiplies by
-  for (uint32_t s = 0; s < n_scenes; ++s) {
+  const uint32_t L = sh_kmax + 2u;
+  for (SfwScratch::Worker &w : X.w)
+    w.cull_skipped = w.cull_tests = 0;
+
+  // One scene, start to finish: obstacle clusters, the pedestrian order that goes with them, group table, scene
+  // record, pedestrian pairs, footprint, costmap slot, its slices of the sharing tables.  Scenes write disjoint
+  // ranges of the arena, so any number of workers may run this at once.
+  auto pack_scene = [&](uint32_t s, unsigned wi) {
+    SfwScratch::Worker &W = X.w[wi];
     const SfwScene &sc = scenes[s];
     const SfwRobot &R = sc.robot;
+    const uint32_t pP = X.off_pairs[s], pM = X.off_obst[s], pF = X.off_fp[s];
+    // -- obstacle clusters + pedestrian order.  Obstacle points are stored as compact clusters a pedestrian PAIR
+    // skips when both members are out of reach (obstacle_sum2).  Pedestrians are therefore packed in the order of
+    // the clusters they reach from their start positions, so that the two members of a pair (and neighbouring
+    // pairs: the lanes of the block-per-trajectory kernel) skip the same clusters.  Any order is a valid one: the
+    // social force sums over all others.
+    float r_max = (float)R.agent_radius;
+    for (uint32_t j = 0; j < sc.n_peds; ++j)
+      r_max = std::max(r_max, (float)sc.peds[j].radius);
+    W.pts.resize(sc.n_obstacles);
+    for (uint32_t k = 0; k < sc.n_obstacles; ++k)
+      W.pts[k] = make_float2((float)((sc.obstacles_xy[2 * k] - R.x) * c_obs_d),
+                             (float)((sc.obstacles_xy[2 * k + 1] - R.y) * c_obs_d));
+    float2 *rec = hO + pM;
+    pack_obstacles(W.pts, rec, c->obst_cutoff_log2, (double)r_max * c_obs_d, W.idx);
+    const uint32_t slots = sfw_obst_slots(sc.n_obstacles), n_cl = slots / SFW_OBST_CLUSTER_SLOTS;
+    W.order.resize(sc.n_peds);
+    W.slot.resize(sc.n_peds);
+    uint32_t *order = W.order.data();
+    for (uint32_t j = 0; j < sc.n_peds; ++j)
+      order[j] = j;
+    if (c->obst_cutoff_log2 > 0.0 && n_cl && sc.n_peds) {
+      const uint32_t words = (n_cl + 63u) / 64u;
+      std::vector<uint64_t> &reach = W.reach; // per pedestrian: bit g = cluster g within reach
+      std::vector<uint32_t> &reach_n = W.reach_n;
+      reach.assign((size_t)sc.n_peds * words, 0ull);
+      reach_n.assign(sc.n_peds, 0u);
+      for (uint32_t j = 0; j < sc.n_peds; ++j) {
+        const float qx = (float)(sc.peds[j].x - R.x) * (float)c_obs_d, qy = (float)(sc.peds[j].y - R.y) * (float)c_obs_d;
+        for (uint32_t g = 0; g < n_cl; ++g) {
+          const float dx = qx - rec[g * SFW_OBST_CLUSTER_SLOTS].x, dy = qy - rec[g * SFW_OBST_CLUSTER_SLOTS].y;
+          if (dx * dx + dy * dy <= rec[g * SFW_OBST_CLUSTER_SLOTS + 1].x) {
+            reach[(size_t)j * words + g / 64u] |= 1ull << (g & 63u);
+            ++reach_n[j];
+          }
+        }
+      }
+      std::sort(order, order + sc.n_peds, [&](uint32_t a, uint32_t b) {
+        if (reach_n[a] != reach_n[b])
+          return reach_n[a] > reach_n[b];
+        for (uint32_t w = 0; w < words; ++w)
+          if (reach[(size_t)a * words + w] != reach[(size_t)b * words + w])
+            return reach[(size_t)a * words + w] < reach[(size_t)b * words + w];
+        return a < b;
+      });
+      // share of (pair, cluster) tests that skip the cluster at the start positions (reported only)
+      for (uint32_t k = 0; k < sc.n_peds; k += 2) {
+        const uint32_t a = order[k], b = (k + 1 < sc.n_peds) ? order[k + 1] : order[k];
+        for (uint32_t w = 0; w < words; ++w) {
+          const uint64_t either = reach[(size_t)a * words + w] | reach[(size_t)b * words + w];
+          W.cull_skipped += (w + 1 < words ? 64u : n_cl - 64u * w) - (uint32_t)__builtin_popcountll(either);
+        }
+        W.cull_tests += n_cl;
+      }
+    }
+    for (uint32_t j = 0; j < sc.n_peds; ++j)
+      W.slot[order[j]] = j; // caller's index -> packed position
+
+    // -- pedestrian groups: lightsfm only applies group forces to groups with >= 2 members
+    uint32_t n_groups = 0;
+    if (X.off_grp[s + 1] > X.off_grp[s]) {
+      std::vector<std::pair<int32_t, uint32_t>> &tagged = W.tagged;
+      tagged.clear();
+      for (uint32_t j = 0; j < sc.n_peds; ++j)
+        if (sc.peds[j].group_id >= 0)
+          tagged.emplace_back(sc.peds[j].group_id, j);
+      std::stable_sort(tagged.begin(), tagged.end(),
+                       [](const std::pair<int32_t, uint32_t> &a, const std::pair<int32_t, uint32_t> &b) { return a.first < b.first; });
+      W.starts.clear();
+      W.members.clear();
+      for (size_t i = 0; i < tagged.size();) {
+        size_t e = i;
+        while (e < tagged.size() && tagged[e].first == tagged[i].first)
+          ++e;
+        if (e - i >= 2) {
+          W.starts.push_back((uint32_t)(W.members.size() / 2));
+          for (size_t m = i; m < e; ++m) {
+            const float rad = (float)sc.peds[tagged[m].second].radius;
+            uint32_t bits;
+            memcpy(&bits, &rad, 4);
+            W.members.push_back(W.slot[tagged[m].second]); // index in the packed order
+            W.members.push_back(bits);
+          }
+        }
+        i = e;
+      }
+      n_groups = (uint32_t)W.starts.size();
+      if (n_groups) {
+        W.starts.push_back((uint32_t)(W.members.size() / 2));
+        uint32_t *g = hG + X.off_grp[s];
+        memcpy(g, W.starts.data(), 4 * W.starts.size());
+        memcpy(g + W.starts.size(), W.members.data(), 4 * W.members.size());
+      }
+    }
+    X.grp_cnt[s] = n_groups;
+
+    // -- the scene record
     SfwSceneDev &d = hs[s];
     memset(&d, 0, sizeof(d));
     d.rx = R.x;
@@ -962,27 +982,26 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     d.a_obs_scale = (float)(obs_norm * std::exp(R.agent_radius * inv_sigma));
     d.size_x = sc.size_x;
     d.size_y = sc.size_y;
-    d.win_x0 = wx0[s];
-    d.win_y0 = wy0[s];
+    d.win_x0 = X.wx0[s];
+    d.win_y0 = X.wy0[s];
     const uint32_t n_pairs = (sc.n_peds + 1) / 2;
-    const uint32_t n_obst_pad = sfw_obst_slots(sc.n_obstacles);
     d.n_peds = sc.n_peds;
     d.n_pairs = n_pairs;
-    d.n_obst = n_obst_pad;
+    d.n_obst = slots;
     d.n_fp = sc.n_footprint;
     d.ped_off = pP;
     d.obs_off = pM;
     d.fp_off = pF;
     d.map_off = slot * s;
     d.goal_mask = 0;
-    d.n_groups = grp_cnt[s];
-    d.grp_off = grp_off[s];
+    d.n_groups = n_groups;
+    d.grp_off = X.off_grp[s];
     {
       double circ = 0.0;
       for (uint32_t k = 0; k < sc.n_footprint; ++k)
         circ = std::max(circ, std::hypot(sc.footprint_xy[2 * k], sc.footprint_xy[2 * k + 1]));
-      const double rc = std::floor(circ / sc.resolution) + 2.0;
-      d.fp_rc = (sc.n_footprint >= 3 && rc < 64.0) ? (uint32_t)rc : 0u;
+      const double rcells = std::floor(circ / sc.resolution) + 2.0;
+      d.fp_rc = (sc.n_footprint >= 3 && rcells < 64.0) ? (uint32_t)rcells : 0u;
     }
     // Pedestrian pair (2k, 2k+1): one float4 per quantity = (q0, q1) x (x, y).  An odd crowd is padded
     // with an agent SFW_FAR_AWAY from everything: all its pair/obstacle terms underflow to exactly 0.
@@ -992,7 +1011,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
         const uint32_t j = 2 * k + hlf;
         float *v = q[hlf];
         if (j < sc.n_peds) {
-          const SfwPed &p = sc.peds[ped_order[ped_first[s] + j]];
+          const SfwPed &p = sc.peds[order[j]];
           v[0] = (float)(p.x - R.x);
           v[1] = (float)(p.y - R.y);
           v[2] = (float)p.vx;
@@ -1018,13 +1037,20 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
       hPar[pP + k] = make_float4(q[0][6], q[1][6], q[0][7], q[1][7]);
       hPar2[pP + k] = make_float4(q[0][8], q[1][8], q[0][9], q[1][9]);
     }
-    pP += n_pairs;
-    // obstacle points: scene frame, pre-multiplied by log2(e)/sigma, clustered (packed above)
-    memcpy(hO + pM, obs_packed.data() + pM, sizeof(float2) * n_obst_pad);
-    pM += n_obst_pad;
     for (uint32_t k = 0; k < sc.n_footprint; ++k)
       hF[pF + k] = make_double2(sc.footprint_xy[2 * k], sc.footprint_xy[2 * k + 1]);
-    pF += sc.n_footprint;
+    // -- this scene's slices of the sharing tables
+    if (share_candidate) {
+      memcpy(h + o_skv + 2 * (size_t)s * n_v, X.kv.data() + (size_t)s * n_v, 2 * (size_t)n_v);
+      memcpy(h + o_skw + 2 * (size_t)s * n_w, X.kw.data() + (size_t)s * n_w, 2 * (size_t)n_w);
+      memcpy(h + o_sdv + (size_t)s * n_v, X.dv.data() + (size_t)s * n_v, n_v);
+      memcpy(h + o_sdw + (size_t)s * n_w, X.dw.data() + (size_t)s * n_w, n_w);
+      memcpy(h + o_sperm + 4 * (size_t)s * n_w, X.perm.data() + (size_t)s * n_w, 4 * (size_t)n_w);
+      memcpy(h + o_srperm + 4 * (size_t)s * n_v, X.rperm.data() + (size_t)s * n_v, 4 * (size_t)n_v);
+      memcpy(h + o_slr + 4 * (size_t)s * L, X.lvl_rows.data() + (size_t)s * L, 4 * (size_t)L);
+      memcpy(h + o_slc + 4 * (size_t)s * L, X.lvl_cols.data() + (size_t)s * L, 4 * (size_t)L);
+    }
+    // -- the costmap slot (the bulk of the bytes)
     uint8_t *dst = h + o_maps + slot * s;
     if (sc.size_x == map_pitch) {
       memcpy(dst, sc.costmap, (size_t)sc.size_x * sc.size_y);
@@ -1032,11 +1058,32 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
       for (uint32_t r = 0; r < sc.size_y; ++r)
         memcpy(dst + (size_t)r * map_pitch, sc.costmap + (size_t)r * sc.size_x, sc.size_x);
     }
+  };
+
+  // Big batches go to the device in pieces: while the workers pack the next piece of scenes, the costmap slots of
+  // the previous one are already on their way (one H2D per piece on the context stream; everything that is not
+  // a costmap — a few per cent of the bytes — follows in one copy at the end).
+  const uint32_t piece = (slot * n_scenes > ((size_t)16 << 20)) ? std::max<uint32_t>(1u, (uint32_t)(((size_t)8 << 20) / slot)) : n_scenes;
+  if (piece >= n_scenes) {
+    c->pool.run(n_scenes, pack_scene, 8);
+    CK(c, cudaMemcpyAsync(c->in.dev, c->in.host, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    for (uint32_t s0 = 0; s0 < n_scenes; s0 += piece) {
+      const uint32_t cnt = std::min(piece, n_scenes - s0);
+      c->pool.run(cnt, [&](uint32_t i, unsigned wi) { pack_scene(s0 + i, wi); }, 8);
+      CK(c, cudaMemcpyAsync(c->in.dev + o_maps + slot * s0, c->in.host + o_maps + slot * s0, slot * cnt,
+                            cudaMemcpyHostToDevice, c->stream));
+    }
+    CK(c, cudaMemcpyAsync(c->in.dev, c->in.host, o_maps, cudaMemcpyHostToDevice, c->stream));
   }
-  CK(c, cudaMemcpyAsync(c->in.dev, c->in.host, in_bytes, cudaMemcpyHostToDevice, c->stream));
   CK(c, cudaEventRecord(c->h2d_done, c->stream));
   c->in_bytes = in_bytes;
   c->scene_host.assign(hs, hs + n_scenes);
+  uint64_t cull_skipped = 0, cull_tests = 0;
+  for (const SfwScratch::Worker &w : X.w) {
+    cull_skipped += w.cull_skipped;
+    cull_tests += w.cull_tests;
+  }
 
   // ---- outputs -------------------------------------------------------------------------------
   const uint32_t max_tiles = (samples + 31) / 32; // any slab / block size fits
@@ -1145,7 +1192,7 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     B.share.row_perm = reinterpret_cast<const uint32_t *>(dv + o_srperm);
     B.share.lvl_rows = reinterpret_cast<const uint32_t *>(dv + o_slr);
     B.share.lvl_cols = reinterpret_cast<const uint32_t *>(dv + o_slc);
-    B.share.chunk_map = sh_chunk_map.empty() ? nullptr : reinterpret_cast<const uint32_t *>(dv + o_scm);
+    B.share.chunk_map = X.chunk_map.empty() ? nullptr : reinterpret_cast<const uint32_t *>(dv + o_scm);
     B.share.scene_stride = (uint64_t)share_paths * (sh_kmax + 1u) * share_rec;
     B.share.rec_bytes = share_rec;
     B.share.kmax = sh_kmax;
@@ -1174,6 +1221,18 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   c->slab_begin = 0;
   c->slab_end = 0xffffffffu;
   c->staged = true;
+  return SFW_OK;
+}
+
+int sfw_set_host_threads(sfw_ctx *c, int n_threads) {
+  if (!c)
+    return SFW_ERR_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (n_threads < 1 || n_threads > 64)
+    return fail(c, SFW_ERR_ARG, "sfw_set_host_threads: need 1 <= n_threads <= 64");
+  c->host_threads = n_threads;
+  if (c->pool.size() > (unsigned)n_threads || (unsigned)n_threads == 1u)
+    c->pool.resize((unsigned)n_threads);
   return SFW_OK;
 }
 
@@ -1216,7 +1275,8 @@ uint32_t sfw_obstacle_layout(const double *obstacles_xy, uint32_t n, double ref_
   for (uint32_t k = 0; k < n; ++k)
     pts[k] = make_float2((float)((obstacles_xy[2 * k] - ref_x) * c_obs_d),
                          (float)((obstacles_xy[2 * k + 1] - ref_y) * c_obs_d));
-  pack_obstacles(pts, rec.data(), cutoff_log2, (double)(float)r_max * c_obs_d);
+  std::vector<uint32_t> idx;
+  pack_obstacles(pts, rec.data(), cutoff_log2, (double)(float)r_max * c_obs_d, idx);
   memcpy(slots_out, rec.data(), sizeof(float2) * std::min(slots, slots_cap));
   return slots;
 }
@@ -1419,8 +1479,17 @@ int sfw_download(sfw_ctx *c, float *costs_out, SfwBest *best_out) {
   }
   if (best_out)
     memcpy(best_out, c->out.host + c->off_best, nb);
-  if (costs_out)
-    memcpy(costs_out, c->out.host + c->off_costs, nc);
+  if (costs_out) {
+    // a batch's cost vectors are tens of megabytes: the host workers copy them out of the landing buffer in slices
+    const size_t slice = (size_t)1 << 20;
+    const uint32_t n_slices = (uint32_t)((nc + slice - 1) / slice);
+    const uint8_t *src = c->out.host + c->off_costs;
+    uint8_t *dst = reinterpret_cast<uint8_t *>(costs_out);
+    c->pool.run(n_slices, [&](uint32_t i, unsigned) {
+      const size_t o = (size_t)i * slice;
+      memcpy(dst + o, src + o, std::min(slice, nc - o));
+    }, 8);
+  }
   return SFW_OK;
 }
 

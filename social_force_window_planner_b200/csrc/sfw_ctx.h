@@ -5,10 +5,15 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
+#include <functional>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "sfw_dev.h"
@@ -17,6 +22,110 @@ struct SfwArena {
   uint8_t *host = nullptr; // pinned
   uint8_t *dev = nullptr;
   size_t cap = 0;
+};
+
+// Host worker pool of one context: packs the scenes of a batch in parallel (sfw_upload) and copies big results
+// out of the pinned landing buffer (sfw_download).  run(n, fn) calls fn(item, worker) for item = 0 .. n - 1 with
+// dynamic scheduling; the calling thread is worker 0 and takes part.  Small jobs run inline (no wake-up latency
+// on the single-scene control tick).
+class SfwPool {
+ public:
+  ~SfwPool() { stop(); }
+  unsigned size() const { return (unsigned)th_.size() + 1u; }
+  void resize(unsigned n_threads) { // total workers including the caller
+    stop();
+    quit_ = false;
+    for (unsigned w = 1; w < n_threads; ++w)
+      th_.emplace_back([this, w] { loop(w); });
+  }
+  void run(uint32_t n, const std::function<void(uint32_t, unsigned)> &fn, uint32_t inline_below = 4) {
+    if (n < inline_below || th_.empty()) {
+      for (uint32_t i = 0; i < n; ++i)
+        fn(i, 0u);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      fn_ = &fn;
+      n_ = n;
+      next_.store(0u);
+      busy_ = (unsigned)th_.size();
+      ++gen_;
+    }
+    cv_.notify_all();
+    work(0u);
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [this] { return busy_ == 0u; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void work(unsigned w) {
+    for (;;) {
+      const uint32_t i = next_.fetch_add(1u);
+      if (i >= n_)
+        break;
+      (*fn_)(i, w);
+    }
+  }
+  void loop(unsigned w) {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return quit_ || gen_ != seen; });
+        if (quit_)
+          return;
+        seen = gen_;
+      }
+      work(w);
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        if (--busy_ == 0u)
+          done_.notify_one();
+      }
+    }
+  }
+  void stop() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      quit_ = true;
+    }
+    cv_.notify_all();
+    for (std::thread &t : th_)
+      t.join();
+    th_.clear();
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(uint32_t, unsigned)> *fn_ = nullptr;
+  uint32_t n_ = 0;
+  std::atomic<uint32_t> next_{0};
+  unsigned busy_ = 0;
+  uint64_t gen_ = 0;
+  bool quit_ = false;
+};
+
+// Scratch of sfw_upload, kept in the context so that a control tick allocates nothing once it has warmed up.
+struct SfwScratch {
+  std::vector<uint32_t> off_pairs, off_obst, off_fp, off_grp, off_ped; // per-scene prefix offsets [n_scenes + 1]
+  std::vector<uint32_t> grp_cnt;                                       // groups (>= 2 members) per scene
+  std::vector<int32_t> wx0, wy0;
+  std::vector<uint16_t> kv, kw;
+  std::vector<uint8_t> dv, dw;
+  std::vector<uint32_t> perm, rperm, lvl_rows, lvl_cols, chunk_map;
+  struct Worker {
+    std::vector<float2> pts, rec;
+    std::vector<uint64_t> reach;
+    std::vector<uint32_t> reach_n, order, slot, idx, starts, members, cur;
+    std::vector<std::pair<int32_t, uint32_t>> tagged;
+    std::vector<double> up, dn;
+    uint64_t cull_skipped = 0, cull_tests = 0;
+    uint32_t kmax = 0;
+    double tot = 0.0;
+  };
+  std::vector<Worker> w;
 };
 
 struct SfwPlan {
@@ -39,6 +148,9 @@ struct sfw_ctx {
   std::string err;
   std::mutex mu;
 
+  int host_threads = 1; // workers a batch is packed with (sfw_set_host_threads); set from the host at sfw_create
+  SfwPool pool;       // host workers, started by the first batch of >= 8 scenes
+  SfwScratch scratch; // sfw_upload's reusable buffers
   SfwArena in;   // packed inputs
   SfwArena out;  // best | costs | npts | blockbest | counters
   SfwArena sensor_in, sensor_out; // sfw_laser_obstacles / sfw_marker_points staging

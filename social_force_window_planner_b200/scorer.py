@@ -70,6 +70,10 @@ class Scorer:
         """Kernel selection policy (``sfw_set_policy``): AUTO switches small grids to the low-latency kernel."""
         self._check(self._lib.sfw_set_policy(self._ctx, policy))
 
+    def set_host_threads(self, n_threads: int):
+        """``sfw_set_host_threads``: host workers that pack a batch of scenes (1 = the calling thread only)."""
+        self._check(self._lib.sfw_set_host_threads(self._ctx, int(n_threads)))
+
     def set_zero_sample(self, score_it: bool):
         """``sfw_set_zero_sample``: score the (0,0) sample (single scoreTrajectory calls of the reference) instead
         of skipping it (its grid loop)."""

@@ -554,3 +554,37 @@ def test_may_i_stop_matches_reference(scorer):
             n = int(np.ceil(g["args"][0] / (p.max_trans_acc * g["dt"]) - 1e-9))  # subtractions leave a residue)
             assert steps in (n, n + 1), (g, steps)
     assert seen == {0, 1}
+
+
+def test_parallel_packing_is_bit_identical():
+    """A batch is packed by the context's host workers (sfw_set_host_threads), one scene per work item, and shipped
+    in pieces.  Ragged scenes (pedestrian / obstacle counts, map sizes, footprints, group tags in some scenes only):
+    1, 3 and 8 workers must produce the same bits, and the same as single-scene calls."""
+    from social_force_window_planner_b200.scorer import Scorer
+    wl = dataclasses.replace(S.WORKLOADS["C3"], n_v=40, n_w=40)  # 1600 samples: sharing tables are built too
+    scs = []
+    for k in range(37):
+        w2 = dataclasses.replace(wl, map_w=120 + 8 * (k % 5), map_h=100 + 12 * (k % 4))
+        sc = S.make_scene(w2, k, n_peds=(k * 7) % 23, n_obstacles=(k * 5) % 41, hazards=(k % 6 == 0),
+                          footprint=None if k % 3 else S.circle_footprint(0.3, 7 + k % 9))
+        if k % 4 == 1 and len(sc.peds) >= 6:
+            sc.peds["group_id"][:6] = np.arange(6) // 3
+        scs.append(sc)
+    p = wl.params()
+    lin, ang = wl.sample_arrays()
+    res = {}
+    for n in (1, 3, 8):
+        s2 = Scorer(0)
+        try:
+            s2.set_policy(Scorer.POLICY_THROUGHPUT)
+            s2.set_host_threads(n)
+            res[n] = s2.score(p, scs, lin, ang)
+            if n == 1:
+                for k in (0, 5, 13, 36):
+                    c1, b1 = s2.score(p, [scs[k]], lin, ang)
+                    assert np.array_equal(c1[0], res[1][0][k]) and b1[0] == res[1][1][k], k
+        finally:
+            s2.close()
+    for n in (3, 8):
+        assert np.array_equal(res[n][0], res[1][0]) and np.array_equal(res[n][1], res[1][1]), n
+    parity.compare(p, scs[13], lin, ang, res[8][0][13], res[8][1][13])
