@@ -29,6 +29,13 @@ geometry_msgs::msg::PoseStamped pose_of(const std::string &frame, double x, doub
 }
 } // namespace
 
+// The same harness drives the reference's own planner core (entry sfw_ref_node_run) and — compiled against
+// plugin/include, where social_force_window_planner/sfw_planner.hpp is the B200 core — the reference's UNMODIFIED
+// node + sensor interface on top of plugin/src/sfw_planner.cpp (entry sfw_dropin_node_run, Makefile target dropin).
+#ifndef SFW_NODE_ENTRY
+#define SFW_NODE_ENTRY sfw_ref_node_run
+#endif
+
 extern "C" {
 
 // scene: costmap + footprint (+ robot.wpx.. unused).  ranges/people/odom as in ref_sensor_harness.cpp (all in the
@@ -36,7 +43,7 @@ extern "C" {
 // "odom" by tf = {x, y, yaw}).  ticks: computeVelocityCommands is called `ticks` times on the same inputs
 // (waypoint bookkeeping and path pruning carry over).  Outputs per tick t: cmd_out[3t..] = twist (vx, vy, wz),
 // status_out[t] = 1 ok / 0 zero twist / -1 PlannerException; plan_left_out[t] = poses left in the pruned plan.
-int sfw_ref_node_run(const SfwParams *params, const double *ext, const SfwScene *scene, const float *ranges,
+int SFW_NODE_ENTRY(const SfwParams *params, const double *ext, const SfwScene *scene, const float *ranges,
                      uint32_t n_ranges, float angle_min, float angle_inc, const double *people, uint32_t n_people,
                      const double *odom, const double *plan_xyt, uint32_t n_plan, int plan_has_tf, const double *tf,
                      uint32_t ticks, double *cmd_out, int *status_out, int *plan_left_out, int *goal_reached_out) {

@@ -15,6 +15,7 @@ public:
     return mx < size_x_ && my < size_y_;
   }
   unsigned char getCost(unsigned int mx, unsigned int my) const { return costmap_[my * size_x_ + mx]; }
+  unsigned char *getCharMap() const { return const_cast<unsigned char *>(costmap_); } // nav2: the raw grid
   unsigned int getSizeInCellsX() const { return size_x_; }
   unsigned int getSizeInCellsY() const { return size_y_; }
   double getResolution() const { return resolution_; }

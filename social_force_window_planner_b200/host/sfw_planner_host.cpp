@@ -8,33 +8,10 @@
 
 namespace social_force_window_planner {
 
-namespace {
-// reference sfw_planner.hpp:399-407 (all-float arithmetic)
-inline float normalizeAngle(float val, float min, float max) {
-  float norm = 0.0f;
-  if (val >= min)
-    norm = min + fmodf((val - min), (max - min));
-  else
-    norm = max - fmodf((min - val), (max - min));
-  return norm;
-}
-} // namespace
-
 SFWPlanner::SFWPlanner(const ControllerParams &params, const CostmapView *costmap,
                        std::vector<Point2D> footprint_spec, int device)
     : params_(params), costmap_(costmap), footprint_spec_(std::move(footprint_spec)), device_(device) {
-  // sample sets, reference sfw_planner.cpp:65-85
-  const int n_linvels = 4;
-  const double linvel_step = params_.max_vel_x_ / n_linvels;
-  for (int i = 0; i <= n_linvels; i++)
-    linvels_.push_back(i * linvel_step);
-  const int n_angvels = 4;
-  const double angvel_step = params_.max_vel_th_ / n_angvels;
-  angvels_.push_back(0.0);
-  for (int i = 1; i <= n_angvels; i++) {
-    angvels_.push_back(i * angvel_step);
-    angvels_.push_back(i * (-angvel_step));
-  }
+  sfw_host::default_sample_sets(params_.max_vel_x_, params_.max_vel_th_, linvels_, angvels_); // :65-85
 }
 
 SFWPlanner::~SFWPlanner() {
@@ -235,171 +212,73 @@ std::vector<Marker> SFWPlanner::getMarkerArray() {
   return out;
 }
 
-// reference src/sfw_planner.cpp:117-469
+// One control tick (reference src/sfw_planner.cpp:117-469).  What kind of tick this is — idle, goal reached, turn
+// in place, approach, sample grid — and the command / waypoint that go with it is decided by sfw_host::PlanTracker
+// (sfw_tick.hpp, shared with the ROS-typed plugin class in plugin/src/sfw_planner.cpp); this function only talks to
+// the scorer: one sfw_score call for a proposal that has to be legal, one for the grid.
 bool SFWPlanner::findBestAction(const Pose2D &global_pose, const Twist2D &global_vel, Twist2D &cmd_vel) {
-  goal_reached_ = false;
-  double vx, vy = 0.0, vt;
   best_i_ = -1;
+  // the reference narrows the robot state to float first (:145-152)
+  const float rx = global_pose.x, ry = global_pose.y, rt = global_pose.yaw;
+  const float rvx = global_vel.linear_x, rvy = global_vel.linear_y, rvt = global_vel.angular_z;
 
-  if (!running_) { // :131-142
-    cmd_vel.linear_x = 0.0;
-    cmd_vel.linear_y = 0.0;
-    cmd_vel.angular_z = 0.0;
+  sfw_host::TickLimits lim;
+  lim.max_vel_x = params_.max_vel_x_, lim.min_vel_x = params_.min_vel_x_;
+  lim.max_vel_th = params_.max_vel_th_, lim.min_vel_th = params_.min_vel_th_;
+  lim.min_in_place_vel_th = params_.min_in_place_vel_th_;
+  lim.yaw_goal_tolerance = params_.yaw_goal_tolerance_, lim.xy_goal_tolerance = params_.xy_goal_tolerance_;
+  lim.wp_tolerance = params_.wp_tolerance_;
+  lim.is_circular = params_.is_circular_;
+
+  using sfw_host::TickKind;
+  const sfw_host::TickPlan tick = tracker_.next(rx, ry, rt, lim);
+  cmd_vel.linear_x = tick.vx;
+  cmd_vel.linear_y = tick.vy;
+  cmd_vel.angular_z = tick.vth;
+  if (tick.kind == TickKind::Idle || tick.kind == TickKind::GoalReached)
     return true;
+
+  SfwBest best;
+  if (tick.kind == TickKind::TurnInPlace) {
+    if (!tick.needs_scoring)
+      return true;
+    const double lin = tick.vx, ang = tick.vth; // a non-circular base must be able to sweep the turn (:199-218)
+    return score(rx, ry, rt, rvx, rvy, rvt, 0.0, 0.0, &lin, 1, &ang, 1, costs_, best) && !(costs_[0] < 0.0f);
   }
-
-  // robot state narrowed to float exactly like the reference (:145-152)
-  float rx, ry, rt, rvx, rvy, rvt;
-  rx = global_pose.x;
-  ry = global_pose.y;
-  rt = global_pose.yaw;
-  rvx = global_vel.linear_x;
-  rvy = global_vel.linear_y;
-  rvt = global_vel.angular_z;
-
-  double dist_goal_sq = (rx - goal_x_) * (rx - goal_x_) + (ry - goal_y_) * (ry - goal_y_); // :167
-
-  if (dist_goal_sq < (params_.xy_goal_tolerance_ * params_.xy_goal_tolerance_)) { // :176-233
-    vx = 0.0;
-    if (fabs(goal_t_ - rt) < params_.yaw_goal_tolerance_) {
-      vt = 0.0;
-      running_ = false;
-      goal_reached_ = true;
-    } else {
-      float ang_diff = goal_t_ - rt;
-      ang_diff = normalizeAngle(ang_diff, -M_PI, M_PI);
-      if (ang_diff > 0.0)
-        vt = params_.min_in_place_vel_th_;
-      else
-        vt = -params_.min_in_place_vel_th_;
-      if (!params_.is_circular_) { // the rotation must be collision free: one scored trajectory
-        SfwBest b;
-        const double lin = vx, ang = vt;
-        const bool ok = score(rx, ry, rt, rvx, rvy, rvt, 0.0, 0.0, &lin, 1, &ang, 1, costs_, b);
-        if (!ok || costs_[0] < 0.0f) {
-          cmd_vel.linear_x = vx;
-          cmd_vel.linear_y = vy;
-          cmd_vel.angular_z = vt;
-          return false;
-        }
-      }
-    }
-    cmd_vel.linear_x = vx;
-    cmd_vel.linear_y = vy;
-    cmd_vel.angular_z = vt;
-    return true;
-  }
-
-  if (new_plan_) { // closest point of a fresh plan (:236-257)
-    new_plan_ = false;
-    double dist_sq;
-    double min_dist = 9999.0;
-    wp_index_ = 0;
-    for (int i = (int)global_plan_.size() - 1; i >= 0; i--) {
-      double wpx = global_plan_[i].x;
-      double wpy = global_plan_[i].y;
-      dist_sq = (rx - wpx) * (rx - wpx) + (ry - wpy) * (ry - wpy);
-      if (dist_sq < (params_.wp_tolerance_ * params_.wp_tolerance_)) {
-        wp_index_ = i;
-        break;
-      } else if (dist_sq < min_dist) {
-        min_dist = dist_sq;
-        wp_index_ = i;
-      }
-    }
-  }
-
-  double wpx = global_plan_[wp_index_].x; // :260-273
-  double wpy = global_plan_[wp_index_].y;
-  double dist_swp_sq = (rx - wpx) * (rx - wpx) + (ry - wpy) * (ry - wpy);
-  while (dist_swp_sq < (params_.wp_tolerance_ * params_.wp_tolerance_) &&
-         wp_index_ < (int)global_plan_.size() - 1) {
-    wp_index_++;
-    wpx = global_plan_[wp_index_].x;
-    wpy = global_plan_[wp_index_].y;
-    dist_swp_sq = (rx - wpx) * (rx - wpx) + (ry - wpy) * (ry - wpy);
-  }
-
-  double dx = (wpx - rx) * cos(rt) + (wpy - ry) * sin(rt); // :276-278
-  double dy = -(wpx - rx) * sin(rt) + (wpy - ry) * cos(rt);
-  double dt = atan2(dy, dx);
-
-  double dist_thres = 1.5; // approach branch (:282-334)
-  if (dist_goal_sq < (dist_thres * dist_thres)) {
-    vx = params_.min_vel_x_ + (params_.max_vel_x_ - params_.min_vel_x_) * (sqrt(dist_goal_sq) / dist_thres);
-    vy = 0.0;
-    vt = params_.min_vel_th_ + (params_.max_vel_th_ - params_.min_vel_th_) * fabs(dt) / M_PI;
-    if (dt < 0.0)
-      vt *= -1;
-    SfwBest b;
-    const double lin = vx, ang = vt;
-    if (score(rx, ry, rt, rvx, rvy, rvt, wpx, wpy, &lin, 1, &ang, 1, costs_, b) && costs_[0] >= 0.0f) {
-      cmd_vel.linear_x = vx;
-      cmd_vel.linear_y = vy;
-      cmd_vel.angular_z = vt;
-      markers_.assign(1, SampleMarker{vx, vt, costs_[0]});
+  if (tick.kind == TickKind::Approach) {
+    const double lin = tick.vx, ang = tick.vth;
+    if (score(rx, ry, rt, rvx, rvy, rvt, tick.wpx, tick.wpy, &lin, 1, &ang, 1, costs_, best) && costs_[0] >= 0.0f) {
+      markers_.assign(1, SampleMarker{tick.vx, tick.vth, costs_[0]});
       best_i_ = 0;
       return true;
     }
   }
 
-  // the (v, w) grid (:338-417): ONE launch; the arg-min with the reference's tie-breaks comes back
-  SfwBest best;
-  if (!score(rx, ry, rt, rvx, rvy, rvt, wpx, wpy, linvels_.data(), (uint32_t)linvels_.size(), angvels_.data(),
-             (uint32_t)angvels_.size(), costs_, best)) {
-    cmd_vel.linear_x = 0.0;
-    cmd_vel.linear_y = 0.0;
-    cmd_vel.angular_z = 0.0;
+  // the (v, w) grid (:338-417): ONE launch; the arg-min with the reference's tie-breaks comes back with it
+  cmd_vel.linear_x = cmd_vel.linear_y = cmd_vel.angular_z = 0.0;
+  if (!score(rx, ry, rt, rvx, rvy, rvt, tick.wpx, tick.wpy, linvels_.data(), (uint32_t)linvels_.size(), angvels_.data(),
+             (uint32_t)angvels_.size(), costs_, best))
     return false;
-  }
   markers_.resize(costs_.size());
   for (size_t i = 0; i < costs_.size(); ++i)
     markers_[i] = SampleMarker{linvels_[i / angvels_.size()], angvels_[i % angvels_.size()], costs_[i]};
-
-  if (best.valid) { // :426-454
-    best_i_ = (int)best.index;
-    cmd_vel.linear_x = best.v;
-    cmd_vel.linear_y = 0.0;
-    cmd_vel.angular_z = best.w;
-    return true;
-  }
-  cmd_vel.linear_x = 0.0; // :456-468
-  cmd_vel.linear_y = 0.0;
-  cmd_vel.angular_z = 0.0;
-  return false;
-}
-
-// reference src/sfw_planner.cpp:853-892
-bool SFWPlanner::updatePlan(const std::vector<Pose2D> &new_plan) {
-  goal_reached_ = false;
-  global_plan_ = new_plan;
-  if (global_plan_.size() == 0) {
-    running_ = false;
-    wp_index_ = -1;
-    return true;
-  }
-  wp_index_ = 0;
-  running_ = true;
-  new_plan_ = true;
-  const Pose2D &goal_pose = global_plan_[global_plan_.size() - 1];
-  goal_x_ = goal_pose.x;
-  goal_y_ = goal_pose.y;
-  goal_t_ = goal_pose.yaw;
-  const Pose2D &start_pose = global_plan_[0];
-  start_x_ = start_pose.x;
-  start_y_ = start_pose.y;
-  start_t_ = start_pose.yaw;
+  if (!best.valid)
+    return false; // nothing legal: zero twist (:456-468)
+  best_i_ = (int)best.index;
+  cmd_vel.linear_x = best.v;
+  cmd_vel.angular_z = best.w;
   return true;
 }
 
-// reference src/sfw_planner.cpp:894-901
-bool SFWPlanner::isGoalReached() {
-  if (goal_reached_) {
-    goal_reached_ = false; // we reset the flag
-    return true;
-  }
-  return goal_reached_;
+bool SFWPlanner::updatePlan(const std::vector<Pose2D> &new_plan) {
+  std::vector<sfw_host::PlanPose> plan(new_plan.size());
+  for (size_t i = 0; i < new_plan.size(); ++i)
+    plan[i] = sfw_host::PlanPose{new_plan[i].x, new_plan[i].y, new_plan[i].yaw};
+  tracker_.setPlan(plan);
+  return true;
 }
+
+bool SFWPlanner::isGoalReached() { return tracker_.consumeGoalFlag(); }
 
 } // namespace social_force_window_planner
 

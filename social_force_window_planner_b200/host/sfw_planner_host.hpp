@@ -7,7 +7,7 @@
 // data-parallel — the (v, w) loop, scoreTrajectory, footprintCost, the lightsfm calls — is NOT here:
 // it is one sfw_score() call into libsfw_b200.so (include/sfw_b200.h).  What stays on the host is the
 // per-tick control flow of findBestAction (goal tolerance, rotate in place, waypoint selection, the
-// approach branch) and the scene packer that turns the sensor interface's agent list
+// approach branch: sfw_tick.hpp, shared with the ROS-typed plugin class of plugin/) and the scene packer that turns the sensor interface's agent list
 // (reference src/sensor_interface.cpp:618-631) into an SfwScene.
 #ifndef SFW_PLANNER_HOST_HPP
 #define SFW_PLANNER_HOST_HPP
@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/sfw_b200.h"
+#include "sfw_tick.hpp"
 
 namespace social_force_window_planner {
 
@@ -93,7 +94,7 @@ public:
   bool findBestAction(const Pose2D &global_pose, const Twist2D &global_vel, Twist2D &cmd_vel);
   bool updatePlan(const std::vector<Pose2D> &new_plan);
   bool isGoalReached();
-  void resetGoal() { goal_reached_ = false; }
+  void resetGoal() { tracker_.clearGoalFlag(); }
   void setFootprint(std::vector<Point2D> footprint) { footprint_spec_ = std::move(footprint); }
   std::vector<Point2D> getFootprint() const { return footprint_spec_; }
 
@@ -121,8 +122,8 @@ public:
   std::vector<Point2D> trajectoryPoints(uint32_t sample_index);
 
   // introspection for tests
-  int wpIndex() const { return wp_index_; }
-  bool running() const { return running_; }
+  int wpIndex() const { return tracker_.waypointIndex(); }
+  bool running() const { return tracker_.running(); }
   const std::string &lastError() const { return error_; }
   uint64_t kernelLaunches() const;
 
@@ -138,15 +139,14 @@ private:
   std::vector<Point2D> footprint_spec_;
   std::vector<Agent> agents_;
   std::vector<double> linvels_, angvels_;
-  std::vector<Pose2D> global_plan_;
+  sfw_host::PlanTracker tracker_; // plan bookkeeping + the decisions of a tick that need no scoring
   std::vector<SampleMarker> markers_;
   std::vector<float> costs_;
   int device_;
   sfw_ctx *ctx_ = nullptr;
   std::string error_;
-  double goal_x_ = 0.0, goal_y_ = 0.0, goal_t_ = 0.0, start_x_ = 0.0, start_y_ = 0.0, start_t_ = 0.0;
-  int wp_index_ = -1, best_i_ = -1;
-  bool running_ = false, new_plan_ = false, goal_reached_ = false, staged_ = false;
+  int best_i_ = -1;
+  bool staged_ = false;
 };
 
 } // namespace social_force_window_planner

@@ -323,3 +323,26 @@ def oracle_argmin(costs, linvels, angvels) -> SfwBest:
     oracle().sfw_oracle_argmin(c64.ctypes.data_as(_dp), lin.ctypes.data_as(_dp), len(lin), ang.ctypes.data_as(_dp),
                                len(ang), C.byref(sb))
     return sb
+
+
+# ---- the drop-in proof: the reference's UNMODIFIED node + sensor interface on top of plugin/src/sfw_planner.cpp ----
+DROPIN_NODE_SO = os.path.join(ORACLE_DIR, "_ref", "libsfw_dropin_node.so")
+_dropin_node = None
+
+
+def have_dropin_node() -> bool:
+    return os.path.exists(DROPIN_NODE_SO)
+
+
+def dropin_node_run(params, ext, scene, scan, people, odom, plan, plan_has_tf=False, tf=(0.0, 0.0, 0.0), ticks=1):
+    """oracle/_ref/libsfw_dropin_node.so (oracle/Makefile target `dropin`): src/sfw_planner_node.cpp and
+    src/sensor_interface.cpp of the reference, compiled unmodified against plugin/include's sfw_planner.hpp, with the
+    B200 planner core (plugin/src/sfw_planner.cpp -> libsfw_b200.so) underneath.  Same call as ref_node_run."""
+    global _dropin_node
+    if _dropin_node is None:
+        lib = C.CDLL(DROPIN_NODE_SO)
+        lib.sfw_dropin_node_run.restype = C.c_int
+        lib.sfw_dropin_node_run.argtypes = NODE_ARGTYPES
+        _dropin_node = lib
+    return node_call(_dropin_node.sfw_dropin_node_run, params, ext, scene, scan, people, odom, plan, plan_has_tf, tf,
+                     ticks)
