@@ -373,6 +373,7 @@ int sfw_create(sfw_ctx **out, int device, void *stream, const SfwLimits *limits)
   }
   memset(c->status, 0, 64);
   c->xchg.status = c->status + 1;
+  c->pdl = getenv("SFW_B200_NO_PDL") == nullptr;
   if (limits) {
     size_t in_est = (size_t)limits->max_scenes *
                         (sizeof(SfwSceneDev) + (size_t)limits->max_peds * 48 +
@@ -1202,6 +1203,11 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     c->share_merged = share_merged;
     c->share_paths = share_paths;
     c->share_mean_s0 = sh_mean_s0;
+    c->share_off_rperm = o_srperm;
+    c->share_off_lvl_rows = o_slr;
+    c->share_kmax = sh_kmax;
+    c->share_rows_begin = 0;
+    c->share_rows_end = n_v;
   }
   c->obst_skip_frac = cull_tests ? (double)cull_skipped / (double)cull_tests : 0.0;
   if (win_wp) {
@@ -1343,6 +1349,35 @@ int sfw_run(sfw_ctx *c) {
     }
     CK(c, cudaMemsetAsync(B.npts, 0, n * 2, c->stream));
   }
+  // Rollout prefix sharing on a row slab (thread-per-trajectory family): the sample launch walks the SLAB's samples in
+  // fork order, so row_perm / lvl_rows must describe the slab's rows.  Rebuilt here (a few KB per scene) whenever
+  // the slab changes; the path launches still write every shared path (columns are not sharded).
+  const bool slab_share = re > rb && c->share_active && !c->plan.crowd && (rb == 0 && re == B.n_v ? true : (uint64_t)(re - rb) * 8u >= B.n_v);
+  if (slab_share && (c->share_rows_begin != rb || c->share_rows_end != re)) {
+    SfwScratch &X = c->scratch;
+    const uint32_t L = c->share_kmax + 2u, n_v = B.n_v;
+    CK(c, cudaEventSynchronize(c->h2d_done)); // the staging arena is ours again
+    uint32_t *hr = reinterpret_cast<uint32_t *>(c->in.host + c->share_off_rperm);
+    uint32_t *hl = reinterpret_cast<uint32_t *>(c->in.host + c->share_off_lvl_rows);
+    std::vector<uint32_t> cur(L);
+    for (uint32_t s = 0; s < B.n_scenes; ++s) {
+      const uint16_t *kvs = X.kv.data() + (size_t)s * n_v;
+      uint32_t *lr = hl + (size_t)s * L, *rp = hr + (size_t)s * n_v;
+      std::fill(lr, lr + L, 0u);
+      for (uint32_t r = rb; r < re; ++r)
+        ++lr[kvs[r] + 1u];
+      for (uint32_t k = 1; k < L; ++k)
+        lr[k] += lr[k - 1u];
+      std::copy(lr, lr + L, cur.begin());
+      for (uint32_t r = rb; r < re; ++r)
+        rp[cur[kvs[r]]++] = r;
+    }
+    CK(c, cudaMemcpyAsync(c->in.dev + c->share_off_rperm, hr, 4 * (size_t)B.n_scenes * n_v, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(c->in.dev + c->share_off_lvl_rows, hl, 4 * (size_t)B.n_scenes * L, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaEventRecord(c->h2d_done, c->stream));
+    c->share_rows_begin = rb;
+    c->share_rows_end = re;
+  }
   // fused winner exchange: this launch writes epoch parity `slot` of every rank's gather buffer
   memset(&B.xchg, 0, sizeof(B.xchg));
   if (c->xchg.connected) {
@@ -1385,7 +1420,7 @@ int sfw_run(sfw_ctx *c) {
                            c->plan.smem, c->stream, true));
     c->launches += sfw_crowd_fuses_argmin(W) ? 1 : 2; // scorer (+ arg-min)
     c->last_kernel = "sfw_score_crowd";
-  } else if (re > rb && c->share_active && rb == 0 && re == B.n_v) {
+  } else if (slab_share) {
     // rollout prefix sharing: the 4 doubly saturated paths, the 2 (n_v + n_w) singly saturated ones (each
     // continuing one of the 4), then every sample from the record of its own fork point
     // (the path launches are latency bound: small blocks, so that every scene's few paths are resident at once --
@@ -1416,17 +1451,19 @@ int sfw_run(sfw_ctx *c) {
     W.share.mode = 2;
     if (c->share_warp & 2u) {
       W.tiles_per_scene = (c->share_paths - 4u + per - 1u) / per;
-      CK(c, sfw_launch_warp_paths(W, c->tmap, smw, c->stream));
+      CK(c, sfw_launch_warp_paths(W, c->tmap, smw, c->stream, c->pdl));
     } else {
       W.tiles_per_scene = (c->share_paths - 4u + T2 - 1u) / T2;
       CK(c, sfw_launch_small(W, c->tmap, T2,
                              sfw_small_smem_bytes(B.win_wp, B.win_h, c->plan.maxP, c->plan.maxM, c->plan.maxF, T2),
-                             c->stream));
+                             c->stream, c->pdl));
     }
     }
     W.share.mode = 3;
     W.tiles_per_scene = B.tiles_per_scene;
-    CK(c, sfw_launch_small(W, c->tmap, c->plan.T, c->plan.smem, c->stream));
+    if (rb != 0 || re != B.n_v)
+      W.share.chunk_map = nullptr; // the dealt order was built for the whole grid's blocks
+    CK(c, sfw_launch_small(W, c->tmap, c->plan.T, c->plan.smem, c->stream, c->pdl));
     c->launches += 3;
     c->last_kernel = sfw_small_kernel_name(c->plan.T, true);
   } else if (re > rb) {

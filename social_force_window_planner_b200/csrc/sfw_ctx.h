@@ -157,6 +157,8 @@ struct sfw_ctx {
   bool laser_attr_set = false;
   int policy = 0; // SFW_POLICY_*
   int score_zero = 0; // sfw_set_zero_sample
+  bool pdl = true;    // launches that continue from the previous launch's records use programmatic dependent launch
+                      // (SFW_B200_NO_PDL=1 in the environment at sfw_create switches it off: A/B measurements)
   unsigned int *status = nullptr; // mapped pinned [16]: [0] scorer kernels (SFW_DEVSTAT_*), [1] winner exchange
   cudaEvent_t h2d_done = nullptr; // the staging buffer `in.host` may be overwritten once this has fired
   double obst_cutoff_log2 = SFW_OBST_CUTOFF_LOG2; // sfw_set_obstacle_cutoff; <= 0: off
@@ -172,6 +174,9 @@ struct sfw_ctx {
   size_t share_cap = 0;
   uint32_t share_paths = 0;
   double share_mean_s0 = 0.0;
+  size_t share_off_rperm = 0, share_off_lvl_rows = 0; // byte offsets of row_perm / lvl_rows in the input arena
+  uint32_t share_kmax = 0;
+  uint32_t share_rows_begin = 0, share_rows_end = 0;  // rows the device tables currently describe
 
   // fused multi-GPU winner exchange (csrc/sfw_exchange.cu)
   struct {

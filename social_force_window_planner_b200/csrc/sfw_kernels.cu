@@ -27,6 +27,7 @@
 //   include/.../world_model.hpp:45-75 + src/costmap_model.cpp:21-121 +
 //   include/.../line_iterator.hpp:37-124 (footprint rasterisation), lightsfm.
 #include <algorithm>
+#include <cstring>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -214,13 +215,15 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
     const size_t R = H.rec_bytes, K1 = (size_t)H.kmax + 1u;
     const uint32_t p = WARP ? ptile * (T >> 5) + (tid >> 5) : tile * T + tid; // writer launches: path number
     if (share_mode == 3u) {
-      // sorted position of this thread (sharing always runs the whole grid: first == 0)
-      uint32_t pos = idx;
+      // sorted position of this thread among the samples of the row slab [row_begin, row_end) (the whole grid
+      // unless the caller shards rows over GPUs: then row_perm / lvl_rows describe the slab's rows only)
+      const uint32_t n_slab = last - first;
+      uint32_t pos = tile * T + tid;
       if (H.chunk_map) {
-        const uint32_t ch = idx >> 5;
-        pos = ch < ((last + 31u) >> 5) ? H.chunk_map[ch] * 32u + (idx & 31u) : last;
+        const uint32_t ch = pos >> 5;
+        pos = ch < ((n_slab + 31u) >> 5) ? H.chunk_map[ch] * 32u + (pos & 31u) : n_slab;
       }
-      in_range = pos < last;
+      in_range = pos < n_slab;
       if (in_range) {
         // level of pos: the largest k with lvl_rows[k] * lvl_cols[k] <= pos
         const uint32_t *lvl_rows = H.lvl_rows + (size_t)scene * (H.kmax + 2u);
@@ -324,6 +327,14 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   double social_work = 0.0, costmap_sum = 0.0;
   int npts = 0;
   const int S = B.num_steps;
+  if (SHARE) {
+    // Everything above — the TMA staging, the free-space map, the fork tables — only read the caller's inputs.
+    // The shared-path records below come from the PREVIOUS launch of this tick: with programmatic dependent
+    // launch this kernel's prologue overlapped that launch's tail, and here it waits for it.
+    if (writer)
+      griddep_launch_dependents();
+    griddep_wait();
+  }
   if (WARP && merged && ck_in) {
     // the record this path continues from is written by tile 0 of the scene in this very launch (a lower block
     // index, hence already dispatched): wait for its flag
@@ -1066,20 +1077,42 @@ cudaError_t sfw_small_max_dynamic_smem(size_t *bytes) {
   return cudaSuccess;
 }
 
+namespace {
+// dependent = true: programmatic dependent launch behind the previous kernel of the stream (the kernel itself
+// calls griddep_wait() before it reads what that kernel wrote)
+cudaError_t launch_small_kernel(SmallKernel fn, uint32_t grid, uint32_t T, size_t smem_bytes, cudaStream_t stream,
+                                const SfwBatchDev &B, const CUtensorMap &tmap, bool dependent) {
+  if (!dependent) {
+    fn<<<grid, T, smem_bytes, stream>>>(B, tmap);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(T);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, fn, B, tmap);
+}
+} // namespace
+
 cudaError_t sfw_launch_small(const SfwBatchDev &B, const CUtensorMap &tmap, uint32_t T,
-                             size_t smem_bytes, cudaStream_t stream) {
+                             size_t smem_bytes, cudaStream_t stream, bool dependent) {
   const uint32_t grid = B.n_scenes * B.tiles_per_scene;
-  small_variant(T, B.share.mode != 0).fn<<<grid, T, smem_bytes, stream>>>(B, tmap);
-  return cudaGetLastError();
+  return launch_small_kernel(small_variant(T, B.share.mode != 0).fn, grid, T, smem_bytes, stream, B, tmap, dependent);
 }
 
 // Path writer with one warp per path (B.share.mode 1 or 2; B.tiles_per_scene = blocks of SFW_PATH_WARP_THREADS / 32
 // paths per scene).
 cudaError_t sfw_launch_warp_paths(const SfwBatchDev &B, const CUtensorMap &tmap, size_t smem_bytes,
-                                  cudaStream_t stream) {
+                                  cudaStream_t stream, bool dependent) {
   const uint32_t grid = B.n_scenes * B.tiles_per_scene;
-  kWarpPath.fn<<<grid, SFW_PATH_WARP_THREADS, smem_bytes, stream>>>(B, tmap);
-  return cudaGetLastError();
+  return launch_small_kernel(kWarpPath.fn, grid, SFW_PATH_WARP_THREADS, smem_bytes, stream, B, tmap, dependent);
 }
 
 cudaError_t sfw_warp_paths_occupancy(size_t smem_bytes, int *blocks_per_sm) {

@@ -12,10 +12,12 @@ cudaError_t sfw_small_max_dynamic_smem(size_t *bytes);
 const char *sfw_small_kernel_name(uint32_t T, bool share = false); // variant a block of T threads dispatches to
 cudaError_t sfw_small_occupancy(uint32_t T, size_t smem_bytes, int *blocks_per_sm);
 cudaError_t sfw_warp_paths_occupancy(size_t smem_bytes, int *blocks_per_sm);
+// dependent: programmatic dependent launch behind the previous kernel of the stream (prefix sharing: the prologue of
+// a launch overlaps the tail of the path launch it continues from)
 cudaError_t sfw_launch_warp_paths(const SfwBatchDev &B, const CUtensorMap &tmap, size_t smem_bytes,
-                                  cudaStream_t stream);
+                                  cudaStream_t stream, bool dependent = false);
 cudaError_t sfw_launch_small(const SfwBatchDev &B, const CUtensorMap &tmap, uint32_t T,
-                             size_t smem_bytes, cudaStream_t stream);
+                             size_t smem_bytes, cudaStream_t stream, bool dependent = false);
 // block-per-trajectory kernel for dense crowds (sfw_crowd.cu) + stand-alone arg-min
 size_t sfw_crowd_smem_bytes(uint32_t P, uint32_t M, uint32_t F, uint32_t S);
 cudaError_t sfw_crowd_prepare(size_t smem_bytes, int *blocks_per_sm);

@@ -588,3 +588,51 @@ def test_parallel_packing_is_bit_identical():
     for n in (3, 8):
         assert np.array_equal(res[n][0], res[1][0]) and np.array_equal(res[n][1], res[1][1]), n
     parity.compare(p, scs[13], lin, ang, res[8][0][13], res[8][1][13])
+
+
+@pytest.mark.parametrize("n_v,n_w,n_scenes,world", [(100, 77, 1, 3), (64, 64, 5, 2), (96, 40, 2, 8)])
+def test_prefix_sharing_on_row_slabs_is_bit_identical(n_v, n_w, n_scenes, world):
+    """Row slabs (multi-GPU strong scaling of one batch) keep rollout prefix sharing: the sample launch walks the
+    slab's own fork order (row tables rebuilt per slab), the path launches are the whole grid's.  Every slab's cost
+    rows must equal the unshared full-grid run bit for bit, the merged winner must be the full grid's, and going
+    back to the full grid afterwards must still work."""
+    from social_force_window_planner_b200 import sharding
+    from social_force_window_planner_b200.scorer import Scorer
+    wl = dataclasses.replace(S.WORKLOADS["C1"], n_v=n_v, n_w=n_w, n_peds=9, steps=40)
+    scs = [S.make_scene(wl, i, hazards=(i == n_scenes - 1 and n_scenes > 1)) for i in range(n_scenes)]
+    for k, sc in enumerate(scs):
+        r = list(sc.robot)
+        r[3] = float(np.float32(0.1 + 0.1 * k))
+        r[5] = float(np.float32(-0.3 + 0.2 * k))
+        r[10] = r[3]
+        sc.robot = tuple(r)
+    p = wl.params()
+    lin, ang = wl.sample_arrays()
+    s2 = Scorer(0)
+    try:
+        s2.set_policy(Scorer.POLICY_THROUGHPUT)
+        s2.set_prefix_sharing(0)
+        full_costs, full_best = s2.score(p, scs, lin, ang)
+        assert "share" not in s2.last_kernel
+        s2.set_prefix_sharing(2)
+        s2.upload(p, scs, lin, ang)
+        recs = []
+        for r in range(world):
+            b, e = sharding.block_partition(n_v, world, r)
+            s2.set_row_slab(b, e)
+            s2.run()
+            c, best = s2.download()
+            assert "share" in s2.last_kernel, (r, s2.last_kernel)
+            c3 = c.reshape(n_scenes, n_v, n_w)
+            f3 = full_costs.reshape(n_scenes, n_v, n_w)
+            assert np.array_equal(c3[:, b:e], f3[:, b:e]), r
+            assert (c3[:, :b] == -2.0).all() and (c3[:, e:] == -2.0).all()
+            recs.append(best)
+        for k in range(n_scenes):
+            assert sharding.merge_winners(np.array([rec[k] for rec in recs])) == full_best[k]
+        s2.set_row_slab(0, n_v)
+        s2.run()
+        c, best = s2.download()
+        assert "share" in s2.last_kernel and np.array_equal(c, full_costs) and np.array_equal(best, full_best)
+    finally:
+        s2.close()
