@@ -1,6 +1,6 @@
 """ctypes mirror of ``include/sfw_b200.h`` (the C ABI of the scorer).
 
-Field order and types must match the header exactly; ``tests/test_abi.py`` checks the struct sizes
+Field order and types must match the header exactly; ``tests/test_abi_cpu.py`` checks the struct sizes
 against the values the C library reports.  The structs follow the reference's own data:
 ``SfwParams`` = ControllerParams fields read on the path (reference
 include/social_force_window_planner/sfw_planner.hpp:55-227), ``SfwPed`` = one sfm::Agent as

@@ -19,7 +19,11 @@
 #define SFW_FAR_AWAY 1.0e15f  /* padding pedestrian / obstacle: every force term underflows to exactly 0 */
 #define SFW_MAX_FOOTPRINT 64
 #define SFW_CROWD_THREADS 256  /* block-per-trajectory kernel (sfw_crowd.cu) */
-#define SFW_MAX_PEDS_CROWD 4096
+/* Block-per-trajectory kernel: the whole crowd of one trajectory lives in one block's shared memory, 208 B per
+ * pedestrian PAIR (position, velocity, goal, 2 parameter words, 8 per-warp reaction rows) + the rollout arrays:
+ * about 2 100 pedestrians at 128 steps on a B200 (227 KB per block).  2048 is the guaranteed limit; between 2048
+ * and the shared-memory ceiling sfw_upload still answers SFW_ERR_UNSUPPORTED with the byte count. */
+#define SFW_MAX_PEDS_CROWD 2048
 #define SFW_MAX_BLOCK_SMALL 512 /* launch bound of the thread-per-trajectory kernel (128 regs/thread) */
 #define SFW_PATH_WARP_THREADS 128 /* block of the warp-per-path record writer: 4 paths */
 

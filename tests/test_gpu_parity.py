@@ -636,3 +636,24 @@ def test_prefix_sharing_on_row_slabs_is_bit_identical(n_v, n_w, n_scenes, world)
         assert "share" in s2.last_kernel and np.array_equal(c, full_costs) and np.array_equal(best, full_best)
     finally:
         s2.close()
+
+
+def test_crowd_kernel_at_its_pedestrian_limit(scorer):
+    """SFW_MAX_PEDS_CROWD = 2048 pedestrians (csrc/sfw_dev.h; the crowd of a trajectory lives in one block's shared
+    memory): a 2048-pedestrian scene scores and meets the oracle, 2049 is refused with SFW_ERR_UNSUPPORTED — never
+    a wrong answer or a crash."""
+    from social_force_window_planner_b200.scorer import SfwError
+    wl = dataclasses.replace(S.WORKLOADS["C2"], n_v=2, n_w=3, steps=6, n_peds=2048, ped_r_max=16.0, ped_sep=0.45,
+                             map_w=800, map_h=800)
+    sc = S.make_scene(wl, 0)
+    p = wl.params()
+    lin, ang = wl.sample_arrays()
+    costs, best = scorer.score(p, [sc], lin, ang)
+    assert scorer.last_kernel == "sfw_score_crowd"
+    st = parity.compare(p, sc, lin, ang, costs[0], best[0])
+    assert st["valid"] >= 1, st
+    wl2 = dataclasses.replace(wl, n_peds=2049)
+    with pytest.raises(SfwError) as ei:
+        scorer.score(p, [S.make_scene(wl2, 0)], lin, ang)
+    assert ei.value.code == -3
+    print(st)
