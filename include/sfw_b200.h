@@ -110,7 +110,10 @@ typedef struct SfwPed {
   double radius;
   int32_t has_goal;
   int32_t group_id; /* -1 = none (sensor_interface.cpp:449) */
-  int32_t id;       /* people tag id; robot id is taken as -1 */
+  int32_t id;       /* people tag id.  Carried for the caller's bookkeeping only: lightsfm's computeForces(agent,
+                     * others) skips an `other` whose id equals the agent's, and the reference never sets the
+                     * robot's id (sfm::Agent::id is uninitialised upstream), so whether a
+                     * pedestrian is skipped there is undefined; here every pedestrian always counts. */
   int32_t reserved0;
 } SfwPed;
 
