@@ -28,9 +28,10 @@ for threads in (1, 2, 4, 8, 16):
         sc.run(); sc.sync(); t3 = time.perf_counter()
         sc.download(); t4 = time.perf_counter()
         t += np.array([t1 - t0, t2 - t1, t3 - t2, t4 - t3])
+    out = sc.score(p, sa, lin, ang)
     t0 = time.perf_counter()
     for _ in range(K):
-        sc.score(p, sa, lin, ang)
+        out = sc.score(p, sa, lin, ang, out=out)  # output buffers reused, as a C/C++ caller's would be
     e2e = (time.perf_counter() - t0) / K
     t *= 1e3 / K
     print(f"{n} scenes, {threads:2d} host workers: upload call {t[0]:.2f} ms (+ {t[1]:.2f} ms until the H2D has landed), "

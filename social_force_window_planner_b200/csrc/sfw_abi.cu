@@ -38,8 +38,10 @@ std::string &sfw_create_error() {
 int sfw_arena_reserve(sfw_ctx *c, SfwArena &a, size_t bytes) {
   if (bytes <= a.cap)
     return SFW_OK;
-  // the stream may still be reading the old buffers
+  // the streams may still be reading the old buffers
   SFW_CK(c, cudaStreamSynchronize(c->stream));
+  if (c->copy_stream)
+    SFW_CK(c, cudaStreamSynchronize(c->copy_stream));
   if (a.host)
     cudaFreeHost(a.host);
   if (a.dev)
@@ -107,6 +109,14 @@ int make_tensor_map(sfw_ctx *c, const uint8_t *maps, uint32_t pitch, uint32_t ro
 }
 
 const SfwSfmParams kDefaultSfm = {2.0, 10.0, 0.2, 2.1, 3.0, 2.0, 1.0, 2.0, 0.35, 2.0, 3.0, 0.5};
+
+// one run = run_prepare (once) + run_launch per range of scenes (defined next to sfw_run)
+struct RunState {
+  uint32_t rb = 0, re = 0;
+  bool slab_share = false;
+};
+int run_prepare(sfw_ctx *c, RunState &rs);
+int run_launch(sfw_ctx *c, const RunState &rs, uint32_t s0, uint32_t cnt);
 
 // Choose block size / tiling for the thread-per-trajectory kernel: maximise resident threads per
 // SM under the shared-memory and register limits, then shrink the block so a single-wave launch
@@ -366,6 +376,12 @@ int sfw_create(sfw_ctx **out, int device, void *stream, const SfwLimits *limits)
   e = cudaHostAlloc((void **)&c->status, 64, cudaHostAllocMapped);
   if (e == cudaSuccess)
     e = cudaEventCreateWithFlags(&c->h2d_done, cudaEventDisableTiming);
+  if (e == cudaSuccess)
+    e = cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming);
+  if (e == cudaSuccess)
+    e = cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming);
+  if (e == cudaSuccess)
+    e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     sfw_fail(nullptr, SFW_ERR_CUDA, "sfw_create: %s", cudaGetErrorString(e));
     sfw_destroy(c);
@@ -423,6 +439,14 @@ int sfw_destroy(sfw_ctx *c) {
     cudaFreeHost(c->status);
   if (c->h2d_done)
     cudaEventDestroy(c->h2d_done);
+  if (c->ev_compute)
+    cudaEventDestroy(c->ev_compute);
+  if (c->ev_copy)
+    cudaEventDestroy(c->ev_copy);
+  if (c->copy_stream) {
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamDestroy(c->copy_stream);
+  }
   if (c->d_points)
     cudaFree(c->d_points);
   if (c->h_points)
@@ -433,9 +457,15 @@ int sfw_destroy(sfw_ctx *c) {
   return SFW_OK;
 }
 
-int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, const SfwScene *scenes,
-               uint32_t n_scenes, const double *linvels, uint32_t n_v, const double *angvels,
-               uint32_t n_w) {
+static int upload_impl(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, const SfwScene *scenes,
+                       uint32_t n_scenes, const double *linvels, uint32_t n_v, const double *angvels, uint32_t n_w,
+                       bool launch_too);
+// sfw_upload proper.  launch_too (sfw_score_batch): a big batch of the thread-per-trajectory family is LAUNCHED
+// piece by piece as its costmaps land on the device — the scorer works on the first scenes while the host workers
+// are still packing the last ones — and the call returns with the run already enqueued (c->ran).
+extern "C++" int upload_impl(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, const SfwScene *scenes,
+                       uint32_t n_scenes, const double *linvels, uint32_t n_v, const double *angvels,
+                       uint32_t n_w, bool launch_too) {
   if (!c)
     return SFW_ERR_ARG;
   std::lock_guard<std::mutex> lk(c->mu);
@@ -833,6 +863,136 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
   if (rc != SFW_OK)
     return rc;
 
+  // ---- outputs -------------------------------------------------------------------------------
+  const double inv_sigma = 1.0 / sfm.force_sigma_obstacle;
+  const uint32_t max_tiles = (samples + 31) / 32; // any slab / block size fits
+  size_t oo = 0;
+  c->off_best = oo;
+  oo = align_up(oo + sizeof(SfwBest) * n_scenes, kAlign);
+  c->off_costs = oo;
+  oo = align_up(oo + 4 * (size_t)samples * n_scenes, kAlign);
+  c->off_npts = oo;
+  oo = align_up(oo + 2 * (size_t)samples * n_scenes, kAlign);
+  c->off_bb = oo;
+  oo = align_up(oo + sizeof(SfwBlockBest) * (size_t)max_tiles * n_scenes, kAlign);
+  c->off_cnt = oo;
+  oo = align_up(oo + 4 * (size_t)n_scenes, kAlign);
+  c->off_work = oo;
+  oo = align_up(oo + 64, kAlign);
+  rc = arena_reserve(c, c->out, oo);
+  if (rc != SFW_OK)
+    return rc;
+  // The tile counters must start at 0 (they self-reset after every launch).  Their offset moves with
+  // the sample count, so clear them on every upload: 4 bytes per scene on the same stream.
+  // (the work / done counters of the block-per-trajectory kernel, right behind them, re-arm themselves too)
+  CK(c, cudaMemsetAsync(c->out.dev + c->off_cnt, 0, c->off_work + 64 - c->off_cnt, c->stream));
+  c->out_scenes = n_scenes;
+  c->out_samples = samples;
+
+  // ---- batch descriptor ------------------------------------------------------------------------
+  SfwBatchDev &B = c->B;
+  memset(&B, 0, sizeof(B));
+  uint8_t *dv = c->in.dev;
+  B.scenes = reinterpret_cast<const SfwSceneDev *>(dv + o_scenes);
+  B.pedPos = reinterpret_cast<const float4 *>(dv + o_pos);
+  B.pedVel = reinterpret_cast<const float4 *>(dv + o_vel);
+  B.pedGoal = reinterpret_cast<const float4 *>(dv + o_goal);
+  B.pedPar = reinterpret_cast<const float4 *>(dv + o_par);
+  B.pedPar2 = reinterpret_cast<const float4 *>(dv + o_par2);
+  B.goal_bits = dv + o_gbits;
+  B.obst = reinterpret_cast<const float2 *>(dv + o_obs);
+  B.footprint = reinterpret_cast<const double2 *>(dv + o_fp);
+  B.groups = reinterpret_cast<const uint32_t *>(dv + o_grp);
+  B.maps = dv + o_maps;
+  B.linvels = reinterpret_cast<const double *>(dv + o_lin);
+  B.angvels = reinterpret_cast<const double *>(dv + o_ang);
+  B.costs = reinterpret_cast<float *>(c->out.dev + c->off_costs);
+  B.npts = reinterpret_cast<uint16_t *>(c->out.dev + c->off_npts);
+  B.best = reinterpret_cast<SfwBest *>(c->out.dev + c->off_best);
+  B.blockbest = reinterpret_cast<SfwBlockBest *>(c->out.dev + c->off_bb);
+  B.counters = reinterpret_cast<unsigned int *>(c->out.dev + c->off_cnt);
+  B.map_pitch = map_pitch;
+  B.map_rows = map_rows;
+  B.n_scenes = n_scenes;
+  B.n_v = n_v;
+  B.n_w = n_w;
+  B.row_begin = 0;
+  B.row_end = n_v;
+  B.tiles_per_scene = c->plan.tiles;
+  B.win_wp = win_wp;
+  B.win_h = win_h;
+  B.num_steps = num_steps;
+  B.score_zero = c->score_zero ? 1u : 0u;
+  B.status = c->status;
+  B.dt = dt;
+  B.max_vel_x = params->max_vel_x;
+  B.acc_x = params->max_trans_acc;
+  B.acc_th = params->max_rot_acc;
+  B.w_vel = params->vel_weight;
+  B.w_dist = params->distance_weight;
+  B.w_ang = params->angle_weight;
+  B.w_map = params->costmap_weight;
+  B.w_soc = params->social_weight;
+  B.rr2 = params->robot_radius * params->robot_radius; // float product (sfw_planner.cpp:617)
+  const double log2e = 1.4426950408889634;
+  B.lambda = (float)sfm.lambda;
+  B.gamma = (float)sfm.gamma;
+  B.c_d = (float)(log2e / sfm.gamma);
+  B.c_np = (float)(sfm.n_prime * sfm.n_prime * log2e);
+  B.c_n = (float)(sfm.n * sfm.n * log2e);
+  B.k_soc = (float)sfm.force_factor_social;
+  B.kd_tau = (float)(sfm.force_factor_desired / sfm.relaxation_time);
+  B.inv_tau = (float)(1.0 / sfm.relaxation_time);
+  B.c_obs = (float)(log2e * inv_sigma);
+  B.dtf = (float)dt;
+  B.k_gaze = (float)sfm.force_factor_group_gaze;
+  B.k_coh = (float)sfm.force_factor_group_coherence;
+  B.k_rep = (float)sfm.force_factor_group_repulsion;
+  // ---- prefix sharing decided above: records + tables ----------------------------------------
+  c->share_active = false;
+  c->share_warp = 0;
+  if (share_on) {
+    if (share_need > c->share_cap) {
+      CK(c, cudaStreamSynchronize(c->stream));
+      if (c->share_buf)
+        cudaFree(c->share_buf);
+      c->share_buf = nullptr;
+      c->share_cap = 0;
+      CK(c, cudaMalloc((void **)&c->share_buf, share_need));
+      CK(c, cudaMemsetAsync(c->share_buf, 0, share_need, c->stream)); // record flags (SfwCkptHdr::epoch) start clear
+      c->share_cap = share_need;
+    }
+    B.share.records = c->share_buf;
+    B.share.kv = reinterpret_cast<const uint16_t *>(dv + o_skv);
+    B.share.kw = reinterpret_cast<const uint16_t *>(dv + o_skw);
+    B.share.dirv = dv + o_sdv;
+    B.share.dirw = dv + o_sdw;
+    B.share.col_perm = reinterpret_cast<const uint32_t *>(dv + o_sperm);
+    B.share.row_perm = reinterpret_cast<const uint32_t *>(dv + o_srperm);
+    B.share.lvl_rows = reinterpret_cast<const uint32_t *>(dv + o_slr);
+    B.share.lvl_cols = reinterpret_cast<const uint32_t *>(dv + o_slc);
+    B.share.chunk_map = X.chunk_map.empty() ? nullptr : reinterpret_cast<const uint32_t *>(dv + o_scm);
+    B.share.scene_stride = (uint64_t)share_paths * (sh_kmax + 1u) * share_rec;
+    B.share.rec_bytes = share_rec;
+    B.share.kmax = sh_kmax;
+    B.share.mode = 0;
+    c->share_active = true;
+    c->share_warp = share_warp;
+    c->share_merged = share_merged;
+    c->share_paths = share_paths;
+    c->share_mean_s0 = sh_mean_s0;
+    c->share_off_rperm = o_srperm;
+    c->share_off_lvl_rows = o_slr;
+    c->share_kmax = sh_kmax;
+    c->share_rows_begin = 0;
+    c->share_rows_end = n_v;
+  }
+  if (win_wp) {
+    rc = make_tensor_map(c, B.maps, map_pitch, map_rows, n_scenes, win_wp, win_h);
+    if (rc != SFW_OK)
+      return rc;
+  }
+
   // ---- pack ----------------------------------------------------------------------------------
   // sfw_upload is asynchronous: the previous call's H2D copy may still be reading the pinned staging buffer
   // (upload(A); run; upload(B) without a sync in between) — wait for that copy, not for the whole stream
@@ -852,7 +1012,6 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     memcpy(h + o_scm, X.chunk_map.data(), 4 * X.chunk_map.size());
   memcpy(h + o_lin, linvels, 8 * (size_t)n_v);
   memcpy(h + o_ang, angvels, 8 * (size_t)n_w);
-  const double inv_sigma = 1.0 / sfm.force_sigma_obstacle;
   const double c_obs_d = (double)(float)(1.4426950408889634 * inv_sigma); // the float the kernel multiplies by
   const uint32_t L = sh_kmax + 2u;
   for (SfwScratch::Worker &w : X.w)
@@ -1051,7 +1210,10 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
       memcpy(h + o_slr + 4 * (size_t)s * L, X.lvl_rows.data() + (size_t)s * L, 4 * (size_t)L);
       memcpy(h + o_slc + 4 * (size_t)s * L, X.lvl_cols.data() + (size_t)s * L, 4 * (size_t)L);
     }
-    // -- the costmap slot (the bulk of the bytes)
+  };
+  // ... and its costmap slot: the bulk of the bytes
+  auto pack_map = [&](uint32_t s, unsigned) {
+    const SfwScene &sc = scenes[s];
     uint8_t *dst = h + o_maps + slot * s;
     if (sc.size_x == map_pitch) {
       memcpy(dst, sc.costmap, (size_t)sc.size_x * sc.size_y);
@@ -1061,159 +1223,69 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
     }
   };
 
-  // Big batches go to the device in pieces: while the workers pack the next piece of scenes, the costmap slots of
-  // the previous one are already on their way (one H2D per piece on the context stream; everything that is not
-  // a costmap — a few per cent of the bytes — follows in one copy at the end).
-  const uint32_t piece = (slot * n_scenes > ((size_t)16 << 20)) ? std::max<uint32_t>(1u, (uint32_t)(((size_t)8 << 20) / slot)) : n_scenes;
-  if (piece >= n_scenes) {
-    c->pool.run(n_scenes, pack_scene, 8);
+  // A small batch (and the single scene of a control tick) is packed in one pass and shipped in one copy on the
+  // context stream.  A big one goes in pieces on the context's COPY stream — 8 MB, 16 MB, 32 MB ... of costmap slots,
+  // each packed by the workers (scene records and costmap in one pass) while the previous piece is on its way —
+  // and, from sfw_score_batch, is LAUNCHED in two groups: the scorer starts on the first quarter of the scenes as
+  // soon as they have landed and runs beside the packing and the copies of the other three quarters.
+  const bool pieces = slot * n_scenes > ((size_t)16 << 20);
+  bool launched = false;
+  if (!pieces) {
+    c->pool.run(n_scenes, [&](uint32_t s, unsigned wi) {
+      pack_scene(s, wi);
+      pack_map(s, wi);
+    }, 8);
     CK(c, cudaMemcpyAsync(c->in.dev, c->in.host, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaEventRecord(c->h2d_done, c->stream));
   } else {
-    for (uint32_t s0 = 0; s0 < n_scenes; s0 += piece) {
-      const uint32_t cnt = std::min(piece, n_scenes - s0);
-      c->pool.run(cnt, [&](uint32_t i, unsigned wi) { pack_scene(s0 + i, wi); }, 8);
-      CK(c, cudaMemcpyAsync(c->in.dev + o_maps + slot * s0, c->in.host + o_maps + slot * s0, slot * cnt,
-                            cudaMemcpyHostToDevice, c->stream));
+    const bool launch_groups = launch_too && !c->plan.crowd;
+    RunState rs;
+    if (launch_groups) {
+      c->slab_begin = 0;
+      c->slab_end = 0xffffffffu;
+      rc = run_prepare(c, rs);
+      if (rc != SFW_OK)
+        return rc;
     }
-    CK(c, cudaMemcpyAsync(c->in.dev, c->in.host, o_maps, cudaMemcpyHostToDevice, c->stream));
+    // the device arena may still be read by what is queued on the context stream: copies start behind it
+    CK(c, cudaEventRecord(c->ev_compute, c->stream));
+    CK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_compute, 0));
+    const uint32_t first_group = launch_groups ? std::max<uint32_t>(1u, (n_scenes + 3u) / 4u) : n_scenes;
+    size_t piece_bytes = (size_t)8 << 20;
+    for (uint32_t g0 = 0; g0 < n_scenes;) {
+      const uint32_t g1 = g0 == 0 ? first_group : n_scenes;
+      for (uint32_t s0 = g0; s0 < g1;) {
+        const uint32_t cnt = std::min<uint32_t>(std::max<uint32_t>(1u, (uint32_t)(piece_bytes / slot)), g1 - s0);
+        c->pool.run(cnt, [&](uint32_t i, unsigned wi) {
+          pack_scene(s0 + i, wi);
+          pack_map(s0 + i, wi);
+        }, 8);
+        CK(c, cudaMemcpyAsync(c->in.dev + o_maps + slot * s0, c->in.host + o_maps + slot * s0, slot * cnt,
+                              cudaMemcpyHostToDevice, c->copy_stream));
+        s0 += cnt;
+        piece_bytes = std::min<size_t>(piece_bytes * 2, (size_t)64 << 20);
+      }
+      // everything that is not a costmap (a few per cent of the bytes), for the scenes packed so far; the second
+      // group's copy re-sends the first group's bytes unchanged
+      CK(c, cudaMemcpyAsync(c->in.dev, c->in.host, o_maps, cudaMemcpyHostToDevice, c->copy_stream));
+      CK(c, cudaEventRecord(c->ev_copy, c->copy_stream));
+      CK(c, cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); // the context stream continues behind this group's copies
+      if (launch_groups) {
+        rc = run_launch(c, rs, g0, g1 - g0);
+        if (rc != SFW_OK)
+          return rc;
+      }
+      g0 = g1;
+    }
+    CK(c, cudaEventRecord(c->h2d_done, c->copy_stream));
+    launched = launch_groups;
   }
-  CK(c, cudaEventRecord(c->h2d_done, c->stream));
   c->in_bytes = in_bytes;
   c->scene_host.assign(hs, hs + n_scenes);
   uint64_t cull_skipped = 0, cull_tests = 0;
   for (const SfwScratch::Worker &w : X.w) {
     cull_skipped += w.cull_skipped;
     cull_tests += w.cull_tests;
-  }
-
-  // ---- outputs -------------------------------------------------------------------------------
-  const uint32_t max_tiles = (samples + 31) / 32; // any slab / block size fits
-  size_t oo = 0;
-  c->off_best = oo;
-  oo = align_up(oo + sizeof(SfwBest) * n_scenes, kAlign);
-  c->off_costs = oo;
-  oo = align_up(oo + 4 * (size_t)samples * n_scenes, kAlign);
-  c->off_npts = oo;
-  oo = align_up(oo + 2 * (size_t)samples * n_scenes, kAlign);
-  c->off_bb = oo;
-  oo = align_up(oo + sizeof(SfwBlockBest) * (size_t)max_tiles * n_scenes, kAlign);
-  c->off_cnt = oo;
-  oo = align_up(oo + 4 * (size_t)n_scenes, kAlign);
-  c->off_work = oo;
-  oo = align_up(oo + 64, kAlign);
-  rc = arena_reserve(c, c->out, oo);
-  if (rc != SFW_OK)
-    return rc;
-  // The tile counters must start at 0 (they self-reset after every launch).  Their offset moves with
-  // the sample count, so clear them on every upload: 4 bytes per scene on the same stream.
-  // (the work / done counters of the block-per-trajectory kernel, right behind them, re-arm themselves too)
-  CK(c, cudaMemsetAsync(c->out.dev + c->off_cnt, 0, c->off_work + 64 - c->off_cnt, c->stream));
-  c->out_scenes = n_scenes;
-  c->out_samples = samples;
-
-  // ---- batch descriptor ------------------------------------------------------------------------
-  SfwBatchDev &B = c->B;
-  memset(&B, 0, sizeof(B));
-  uint8_t *dv = c->in.dev;
-  B.scenes = reinterpret_cast<const SfwSceneDev *>(dv + o_scenes);
-  B.pedPos = reinterpret_cast<const float4 *>(dv + o_pos);
-  B.pedVel = reinterpret_cast<const float4 *>(dv + o_vel);
-  B.pedGoal = reinterpret_cast<const float4 *>(dv + o_goal);
-  B.pedPar = reinterpret_cast<const float4 *>(dv + o_par);
-  B.pedPar2 = reinterpret_cast<const float4 *>(dv + o_par2);
-  B.goal_bits = dv + o_gbits;
-  B.obst = reinterpret_cast<const float2 *>(dv + o_obs);
-  B.footprint = reinterpret_cast<const double2 *>(dv + o_fp);
-  B.groups = reinterpret_cast<const uint32_t *>(dv + o_grp);
-  B.maps = dv + o_maps;
-  B.linvels = reinterpret_cast<const double *>(dv + o_lin);
-  B.angvels = reinterpret_cast<const double *>(dv + o_ang);
-  B.costs = reinterpret_cast<float *>(c->out.dev + c->off_costs);
-  B.npts = reinterpret_cast<uint16_t *>(c->out.dev + c->off_npts);
-  B.best = reinterpret_cast<SfwBest *>(c->out.dev + c->off_best);
-  B.blockbest = reinterpret_cast<SfwBlockBest *>(c->out.dev + c->off_bb);
-  B.counters = reinterpret_cast<unsigned int *>(c->out.dev + c->off_cnt);
-  B.map_pitch = map_pitch;
-  B.map_rows = map_rows;
-  B.n_scenes = n_scenes;
-  B.n_v = n_v;
-  B.n_w = n_w;
-  B.row_begin = 0;
-  B.row_end = n_v;
-  B.tiles_per_scene = c->plan.tiles;
-  B.win_wp = win_wp;
-  B.win_h = win_h;
-  B.num_steps = num_steps;
-  B.score_zero = c->score_zero ? 1u : 0u;
-  B.status = c->status;
-  B.dt = dt;
-  B.max_vel_x = params->max_vel_x;
-  B.acc_x = params->max_trans_acc;
-  B.acc_th = params->max_rot_acc;
-  B.w_vel = params->vel_weight;
-  B.w_dist = params->distance_weight;
-  B.w_ang = params->angle_weight;
-  B.w_map = params->costmap_weight;
-  B.w_soc = params->social_weight;
-  B.rr2 = params->robot_radius * params->robot_radius; // float product (sfw_planner.cpp:617)
-  const double log2e = 1.4426950408889634;
-  B.lambda = (float)sfm.lambda;
-  B.gamma = (float)sfm.gamma;
-  B.c_d = (float)(log2e / sfm.gamma);
-  B.c_np = (float)(sfm.n_prime * sfm.n_prime * log2e);
-  B.c_n = (float)(sfm.n * sfm.n * log2e);
-  B.k_soc = (float)sfm.force_factor_social;
-  B.kd_tau = (float)(sfm.force_factor_desired / sfm.relaxation_time);
-  B.inv_tau = (float)(1.0 / sfm.relaxation_time);
-  B.c_obs = (float)(log2e * inv_sigma);
-  B.dtf = (float)dt;
-  B.k_gaze = (float)sfm.force_factor_group_gaze;
-  B.k_coh = (float)sfm.force_factor_group_coherence;
-  B.k_rep = (float)sfm.force_factor_group_repulsion;
-  // ---- prefix sharing decided above: records + tables ----------------------------------------
-  c->share_active = false;
-  c->share_warp = 0;
-  if (share_on) {
-    if (share_need > c->share_cap) {
-      CK(c, cudaStreamSynchronize(c->stream));
-      if (c->share_buf)
-        cudaFree(c->share_buf);
-      c->share_buf = nullptr;
-      c->share_cap = 0;
-      CK(c, cudaMalloc((void **)&c->share_buf, share_need));
-      CK(c, cudaMemsetAsync(c->share_buf, 0, share_need, c->stream)); // record flags (SfwCkptHdr::epoch) start clear
-      c->share_cap = share_need;
-    }
-    B.share.records = c->share_buf;
-    B.share.kv = reinterpret_cast<const uint16_t *>(dv + o_skv);
-    B.share.kw = reinterpret_cast<const uint16_t *>(dv + o_skw);
-    B.share.dirv = dv + o_sdv;
-    B.share.dirw = dv + o_sdw;
-    B.share.col_perm = reinterpret_cast<const uint32_t *>(dv + o_sperm);
-    B.share.row_perm = reinterpret_cast<const uint32_t *>(dv + o_srperm);
-    B.share.lvl_rows = reinterpret_cast<const uint32_t *>(dv + o_slr);
-    B.share.lvl_cols = reinterpret_cast<const uint32_t *>(dv + o_slc);
-    B.share.chunk_map = X.chunk_map.empty() ? nullptr : reinterpret_cast<const uint32_t *>(dv + o_scm);
-    B.share.scene_stride = (uint64_t)share_paths * (sh_kmax + 1u) * share_rec;
-    B.share.rec_bytes = share_rec;
-    B.share.kmax = sh_kmax;
-    B.share.mode = 0;
-    c->share_active = true;
-    c->share_warp = share_warp;
-    c->share_merged = share_merged;
-    c->share_paths = share_paths;
-    c->share_mean_s0 = sh_mean_s0;
-    c->share_off_rperm = o_srperm;
-    c->share_off_lvl_rows = o_slr;
-    c->share_kmax = sh_kmax;
-    c->share_rows_begin = 0;
-    c->share_rows_end = n_v;
-  }
-  c->obst_skip_frac = cull_tests ? (double)cull_skipped / (double)cull_tests : 0.0;
-  if (win_wp) {
-    rc = make_tensor_map(c, B.maps, map_pitch, map_rows, n_scenes, win_wp, win_h);
-    if (rc != SFW_OK)
-      return rc;
   }
 
   // SURVEY.md 8(d) algorithmic bytes
@@ -1224,10 +1296,17 @@ int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm_in, 
           16ull * sc.n_footprint + 128ull + 4ull * (n_v + n_w) + 4ull * samples + 16ull;
   }
   c->algo_bytes = ab;
+  c->obst_skip_frac = cull_tests ? (double)cull_skipped / (double)cull_tests : 0.0;
   c->slab_begin = 0;
   c->slab_end = 0xffffffffu;
   c->staged = true;
+  c->ran = launched;
   return SFW_OK;
+}
+
+int sfw_upload(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm, const SfwScene *scenes,
+               uint32_t n_scenes, const double *linvels, uint32_t n_v, const double *angvels, uint32_t n_w) {
+  return upload_impl(c, params, sfm, scenes, n_scenes, linvels, n_v, angvels, n_w, false);
 }
 
 int sfw_set_host_threads(sfw_ctx *c, int n_threads) {
@@ -1310,15 +1389,17 @@ int sfw_set_row_slab(sfw_ctx *c, uint32_t row_begin, uint32_t row_end) {
   return SFW_OK;
 }
 
-int sfw_run(sfw_ctx *c) {
-  if (!c)
-    return SFW_ERR_ARG;
-  std::lock_guard<std::mutex> lk(c->mu);
-  if (!c->staged)
-    return fail(c, SFW_ERR_STATE, "sfw_run before sfw_upload");
-  CK(c, cudaSetDevice(c->device));
+extern "C++" {
+namespace {
+
+// What one sfw_run does, in two halves, so that a batch can also be launched piece by piece while the rest of it
+// is still being packed (sfw_score_batch): run_prepare = row slab + fork tables of the slab + winner-exchange
+// bookkeeping (once per run), run_launch = the kernel launches for scenes [s0, s0 + cnt).
+int run_prepare(sfw_ctx *c, RunState &rs) {
   SfwBatchDev &B = c->B;
   const uint32_t rb = std::min(c->slab_begin, B.n_v), re = std::min(c->slab_end, B.n_v);
+  rs.rb = rb;
+  rs.re = re;
   if (rb != B.row_begin || re != B.row_end) {
     // rows outside the slab keep SFW_COST_SKIPPED
     B.row_begin = rb;
@@ -1352,8 +1433,8 @@ int sfw_run(sfw_ctx *c) {
   // Rollout prefix sharing on a row slab (thread-per-trajectory family): the sample launch walks the SLAB's samples in
   // fork order, so row_perm / lvl_rows must describe the slab's rows.  Rebuilt here (a few KB per scene) whenever
   // the slab changes; the path launches still write every shared path (columns are not sharded).
-  const bool slab_share = re > rb && c->share_active && !c->plan.crowd && (rb == 0 && re == B.n_v ? true : (uint64_t)(re - rb) * 8u >= B.n_v);
-  if (slab_share && (c->share_rows_begin != rb || c->share_rows_end != re)) {
+  rs.slab_share = re > rb && c->share_active && !c->plan.crowd && (rb == 0 && re == B.n_v ? true : (uint64_t)(re - rb) * 8u >= B.n_v);
+  if (rs.slab_share && (c->share_rows_begin != rb || c->share_rows_end != re)) {
     SfwScratch &X = c->scratch;
     const uint32_t L = c->share_kmax + 2u, n_v = B.n_v;
     CK(c, cudaEventSynchronize(c->h2d_done)); // the staging arena is ours again
@@ -1378,7 +1459,7 @@ int sfw_run(sfw_ctx *c) {
     c->share_rows_begin = rb;
     c->share_rows_end = re;
   }
-  // fused winner exchange: this launch writes epoch parity `slot` of every rank's gather buffer
+  // fused winner exchange: this run writes epoch parity `slot` of every rank's gather buffer
   memset(&B.xchg, 0, sizeof(B.xchg));
   if (c->xchg.connected) {
     if (B.n_scenes > c->xchg.max_scenes)
@@ -1402,6 +1483,18 @@ int sfw_run(sfw_ctx *c) {
       c->xchg.expected[q] += cnt;
     }
   }
+  return SFW_OK;
+}
+
+// The launches of one run for scenes [s0, s0 + cnt).  The block-per-trajectory family pulls work items of the whole
+// batch from one counter, so it only takes the full range.
+int run_launch(sfw_ctx *c, const RunState &rs, uint32_t s0, uint32_t cnt) {
+  SfwBatchDev &B = c->B;
+  const uint32_t rb = rs.rb, re = rs.re;
+  const bool slab_share = rs.slab_share;
+  const bool whole = s0 == 0 && cnt == B.n_scenes;
+  if (c->plan.crowd && !whole)
+    return fail(c, SFW_ERR_STATE, "internal: the block-per-trajectory family is launched for the whole batch");
   if (re > rb && c->plan.crowd && c->share_active && rb == 0 && re == B.n_v) {
     // rollout prefix sharing, block-per-trajectory flavour: paths, paths, samples (+ arg-min)
     unsigned int *wc = reinterpret_cast<unsigned int *>(c->out.dev + c->off_work);
@@ -1426,6 +1519,8 @@ int sfw_run(sfw_ctx *c) {
     // (the path launches are latency bound: small blocks, so that every scene's few paths are resident at once --
     // but not smaller than 128 threads: the block's prologue, the free-space bit map of the window, is shared work)
     SfwBatchDev W = B;
+    W.scene_base = s0;
+    W.launch_scenes = cnt;
     const uint32_t T1 = 128, T2 = 128;
     const uint32_t per = SFW_PATH_WARP_THREADS / 32u;
     const size_t smw = sfw_small_smem_bytes(B.win_wp, B.win_h, c->plan.maxP, c->plan.maxM, c->plan.maxF,
@@ -1440,24 +1535,24 @@ int sfw_run(sfw_ctx *c) {
       CK(c, sfw_launch_warp_paths(W, c->tmap, smw, c->stream));
       c->launches -= 1; // (3 is added below)
     } else {
-    W.share.mode = 1;
-    W.tiles_per_scene = 1;
-    if (c->share_warp & 1u) // a warp per path, a lane per pedestrian pair
-      CK(c, sfw_launch_warp_paths(W, c->tmap, smw, c->stream));
-    else
-      CK(c, sfw_launch_small(W, c->tmap, T1,
-                             sfw_small_smem_bytes(B.win_wp, B.win_h, c->plan.maxP, c->plan.maxM, c->plan.maxF, T1),
-                             c->stream));
-    W.share.mode = 2;
-    if (c->share_warp & 2u) {
-      W.tiles_per_scene = (c->share_paths - 4u + per - 1u) / per;
-      CK(c, sfw_launch_warp_paths(W, c->tmap, smw, c->stream, c->pdl));
-    } else {
-      W.tiles_per_scene = (c->share_paths - 4u + T2 - 1u) / T2;
-      CK(c, sfw_launch_small(W, c->tmap, T2,
-                             sfw_small_smem_bytes(B.win_wp, B.win_h, c->plan.maxP, c->plan.maxM, c->plan.maxF, T2),
-                             c->stream, c->pdl));
-    }
+      W.share.mode = 1;
+      W.tiles_per_scene = 1;
+      if (c->share_warp & 1u) // a warp per path, a lane per pedestrian pair
+        CK(c, sfw_launch_warp_paths(W, c->tmap, smw, c->stream));
+      else
+        CK(c, sfw_launch_small(W, c->tmap, T1,
+                               sfw_small_smem_bytes(B.win_wp, B.win_h, c->plan.maxP, c->plan.maxM, c->plan.maxF, T1),
+                               c->stream));
+      W.share.mode = 2;
+      if (c->share_warp & 2u) {
+        W.tiles_per_scene = (c->share_paths - 4u + per - 1u) / per;
+        CK(c, sfw_launch_warp_paths(W, c->tmap, smw, c->stream, c->pdl));
+      } else {
+        W.tiles_per_scene = (c->share_paths - 4u + T2 - 1u) / T2;
+        CK(c, sfw_launch_small(W, c->tmap, T2,
+                               sfw_small_smem_bytes(B.win_wp, B.win_h, c->plan.maxP, c->plan.maxM, c->plan.maxF, T2),
+                               c->stream, c->pdl));
+      }
     }
     W.share.mode = 3;
     W.tiles_per_scene = B.tiles_per_scene;
@@ -1468,6 +1563,8 @@ int sfw_run(sfw_ctx *c) {
     c->last_kernel = sfw_small_kernel_name(c->plan.T, true);
   } else if (re > rb) {
     SfwBatchDev W = B;
+    W.scene_base = s0;
+    W.launch_scenes = cnt;
     W.share.mode = 0;
     CK(c, sfw_launch_small(W, c->tmap, c->plan.T, c->plan.smem, c->stream));
     c->launches += 1;
@@ -1481,6 +1578,26 @@ int sfw_run(sfw_ctx *c) {
       c->launches += 1;
     }
   }
+  return SFW_OK;
+}
+
+} // namespace
+} // extern "C++"
+
+int sfw_run(sfw_ctx *c) {
+  if (!c)
+    return SFW_ERR_ARG;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->staged)
+    return fail(c, SFW_ERR_STATE, "sfw_run before sfw_upload");
+  CK(c, cudaSetDevice(c->device));
+  RunState rs;
+  int rc = run_prepare(c, rs);
+  if (rc != SFW_OK)
+    return rc;
+  rc = run_launch(c, rs, 0, c->B.n_scenes);
+  if (rc != SFW_OK)
+    return rc;
   c->ran = true;
   return SFW_OK;
 }
@@ -1533,12 +1650,15 @@ int sfw_download(sfw_ctx *c, float *costs_out, SfwBest *best_out) {
 int sfw_score_batch(sfw_ctx *c, const SfwParams *params, const SfwSfmParams *sfm,
                     const SfwScene *scenes, uint32_t n_scenes, const double *linvels, uint32_t n_v,
                     const double *angvels, uint32_t n_w, float *costs_out, SfwBest *best_out) {
-  int rc = sfw_upload(c, params, sfm, scenes, n_scenes, linvels, n_v, angvels, n_w);
+  // a big batch is launched piece by piece from inside the upload (the scorer overlaps the packing of the rest)
+  int rc = upload_impl(c, params, sfm, scenes, n_scenes, linvels, n_v, angvels, n_w, true);
   if (rc != SFW_OK)
     return rc;
-  rc = sfw_run(c);
-  if (rc != SFW_OK)
-    return rc;
+  if (!c->ran) {
+    rc = sfw_run(c);
+    if (rc != SFW_OK)
+      return rc;
+  }
   return sfw_download(c, costs_out, best_out);
 }
 

@@ -161,6 +161,8 @@ struct sfw_ctx {
                       // (SFW_B200_NO_PDL=1 in the environment at sfw_create switches it off: A/B measurements)
   unsigned int *status = nullptr; // mapped pinned [16]: [0] scorer kernels (SFW_DEVSTAT_*), [1] winner exchange
   cudaEvent_t h2d_done = nullptr; // the staging buffer `in.host` may be overwritten once this has fired
+  cudaStream_t copy_stream = nullptr; // H2D pieces of a big batch (the context stream keeps computing beside them)
+  cudaEvent_t ev_compute = nullptr, ev_copy = nullptr; // context stream -> copy stream, and back
   double obst_cutoff_log2 = SFW_OBST_CUTOFF_LOG2; // sfw_set_obstacle_cutoff; <= 0: off
   double obst_skip_frac = 0.0;                    // of the staged batch, at the start poses
 

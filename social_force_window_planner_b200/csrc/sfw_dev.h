@@ -144,6 +144,9 @@ struct SfwBatchDev {
   unsigned int *counters;  // [n_scenes] tiles finished (self-resetting)
   uint32_t map_pitch, map_rows;
   uint32_t n_scenes, n_v, n_w;
+  uint32_t scene_base, launch_scenes; // thread-per-trajectory launches may cover scenes [scene_base, scene_base +
+                                      // launch_scenes) only (a batch is scored piece by piece while the rest of it is
+                                      // still on its way to the device); launch_scenes == 0: all n_scenes
   uint32_t row_begin, row_end; // linvel rows scored by this launch
   uint32_t tiles_per_scene;
   uint32_t win_wp, win_h; // staged window box (padded width, rows); 0 => read the map from global

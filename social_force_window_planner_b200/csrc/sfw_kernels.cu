@@ -65,8 +65,9 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   constexpr bool WARP = SHARE == 2;
   const uint32_t T = blockDim.x;
   const uint32_t tid = threadIdx.x;
-  const uint32_t scene = blockIdx.x / B.tiles_per_scene;
-  const uint32_t tile = blockIdx.x - scene * B.tiles_per_scene;
+  const uint32_t scene_local = blockIdx.x / B.tiles_per_scene;
+  const uint32_t tile = blockIdx.x - scene_local * B.tiles_per_scene;
+  const uint32_t scene = B.scene_base + scene_local; // every index below is the scene's GLOBAL one
   const SfwSceneDev *__restrict__ scp = B.scenes + scene;
   const uint32_t P2 = scp->n_pairs, M = scp->n_obst, F = scp->n_fp;
   const uint32_t n_groups = scp->n_groups;
@@ -1103,7 +1104,7 @@ cudaError_t launch_small_kernel(SmallKernel fn, uint32_t grid, uint32_t T, size_
 
 cudaError_t sfw_launch_small(const SfwBatchDev &B, const CUtensorMap &tmap, uint32_t T,
                              size_t smem_bytes, cudaStream_t stream, bool dependent) {
-  const uint32_t grid = B.n_scenes * B.tiles_per_scene;
+  const uint32_t grid = (B.launch_scenes ? B.launch_scenes : B.n_scenes) * B.tiles_per_scene;
   return launch_small_kernel(small_variant(T, B.share.mode != 0).fn, grid, T, smem_bytes, stream, B, tmap, dependent);
 }
 
@@ -1111,7 +1112,7 @@ cudaError_t sfw_launch_small(const SfwBatchDev &B, const CUtensorMap &tmap, uint
 // paths per scene).
 cudaError_t sfw_launch_warp_paths(const SfwBatchDev &B, const CUtensorMap &tmap, size_t smem_bytes,
                                   cudaStream_t stream, bool dependent) {
-  const uint32_t grid = B.n_scenes * B.tiles_per_scene;
+  const uint32_t grid = (B.launch_scenes ? B.launch_scenes : B.n_scenes) * B.tiles_per_scene;
   return launch_small_kernel(kWarpPath.fn, grid, SFW_PATH_WARP_THREADS, smem_bytes, stream, B, tmap, dependent);
 }
 

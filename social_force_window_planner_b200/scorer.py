@@ -108,16 +108,22 @@ class Scorer:
         return costs, best
 
     # -- one-call form ------------------------------------------------------------------------
-    def score(self, params, scenes, linvels, angvels, sfm=None, want_costs=True):
-        """``sfw_score_batch``: returns (costs[n_scenes, n_v*n_w] float32 or None, best[n_scenes])."""
+    def score(self, params, scenes, linvels, angvels, sfm=None, want_costs=True, out=None):
+        """``sfw_score_batch``: returns (costs[n_scenes, n_v*n_w] float32 or None, best[n_scenes]).
+        ``out`` = (costs, best) of a previous call with the same shapes: the caller's output buffers are reused,
+        as a C/C++ caller of the ABI would (a fresh multi-megabyte array per tick is page-faulted in every time)."""
         sa = scenes if isinstance(scenes, SceneArray) else SceneArray(scenes)
         lin = np.ascontiguousarray(linvels, dtype=np.float64)
         ang = np.ascontiguousarray(angvels, dtype=np.float64)
         self._keep = (sa, lin, ang)
         self.n_scenes = len(sa)
         self.n_samples = len(lin) * len(ang)
-        best = np.zeros(self.n_scenes, dtype=BEST_DTYPE)
-        costs = np.empty((self.n_scenes, self.n_samples), dtype=np.float32) if want_costs else None
+        if out is not None and out[1].shape == (self.n_scenes,) and (
+                not want_costs or (out[0] is not None and out[0].shape == (self.n_scenes, self.n_samples))):
+            costs, best = (out[0] if want_costs else None), out[1]
+        else:
+            best = np.zeros(self.n_scenes, dtype=BEST_DTYPE)
+            costs = np.empty((self.n_scenes, self.n_samples), dtype=np.float32) if want_costs else None
         self._check(self._lib.sfw_score_batch(
             self._ctx, C.byref(params), C.byref(sfm) if sfm else None, sa.ptr(0), len(sa),
             lin.ctypes.data_as(_dp), len(lin), ang.ctypes.data_as(_dp), len(ang),

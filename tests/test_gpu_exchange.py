@@ -179,3 +179,29 @@ def test_missing_peer_is_an_error_not_a_hang():
     finally:
         for s in ring:
             s.close()
+
+
+def test_pipelined_batches_in_a_ring():
+    """Two ranks, each scoring a batch big enough to be launched piece by piece from inside sfw_score_batch: the
+    exchange bookkeeping of a run happens once, before the first piece, and every rank still ends up with all
+    winners."""
+    wl = dataclasses.replace(S.WORKLOADS["C3"], n_v=16, n_w=16)
+    scenes = S.make_scenes(wl, 900)  # 450 per rank x 41.6 KB = 18.7 MB > the 16 MB piece threshold
+    p = wl.params()
+    lin, ang = wl.sample_arrays()
+    ring = _ring(2, 450)
+    ref = Scorer(0)
+    try:
+        ref.set_policy(Scorer.POLICY_THROUGHPUT)
+        _, want = ref.score(p, scenes, lin, ang, want_costs=False)
+        for tick in range(2):
+            for r, s in enumerate(ring):
+                s.set_policy(Scorer.POLICY_THROUGHPUT)
+                _, best = s.score(p, scenes[450 * r:450 * (r + 1)], lin, ang, want_costs=False)
+                assert np.array_equal(best, want[450 * r:450 * (r + 1)])
+            for s in ring:
+                got = s.exchange_fetch()
+                assert np.array_equal(got.reshape(-1), want), tick
+    finally:
+        for s in ring + [ref]:
+            s.close()

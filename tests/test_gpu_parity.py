@@ -657,3 +657,38 @@ def test_crowd_kernel_at_its_pedestrian_limit(scorer):
         scorer.score(p, [S.make_scene(wl2, 0)], lin, ang)
     assert ei.value.code == -3
     print(st)
+
+
+def test_pipelined_batch_equals_staged_batch():
+    """sfw_score_batch launches a big batch piece by piece while the rest of it is still being packed and copied
+    (pieces of 8, 16, 32 ... MB of costmaps); upload + run + download stages everything first.  Same bits either
+    way — with sharing on and off, and for every scene against a single-scene call."""
+    from social_force_window_planner_b200.scorer import Scorer
+    wl = dataclasses.replace(S.WORKLOADS["C3"], n_v=40, n_w=40)   # 640 scenes x 41.6 KB = 26.6 MB of costmaps
+    scs = S.make_scenes(wl, 640)
+    for k, sc in enumerate(scs):
+        r = list(sc.robot)
+        r[3] = float(np.float32(0.05 + 0.6 * (k % 7) / 6.0))
+        r[5] = float(np.float32(-0.4 + 0.8 * (k % 5) / 4.0))
+        r[10] = r[3]
+        sc.robot = tuple(r)
+    p = wl.params()
+    lin, ang = wl.sample_arrays()
+    s2 = Scorer(0)
+    try:
+        for sharing in (1, 0):
+            s2.set_prefix_sharing(sharing)
+            c_pipe, b_pipe = s2.score(p, scs, lin, ang)
+            k_pipe = s2.last_kernel
+            s2.upload(p, scs, lin, ang)
+            s2.run()
+            c_st, b_st = s2.download()
+            assert s2.last_kernel == k_pipe and ("share" in k_pipe) == bool(sharing)
+            assert np.array_equal(c_pipe, c_st) and np.array_equal(b_pipe, b_st), sharing
+        for k in (0, 200, 201, 402, 639):  # first / last scenes of the pieces
+            c1, b1 = s2.score(p, [scs[k]], lin, ang)
+            if s2.last_kernel == k_pipe:
+                assert np.array_equal(c1[0], c_pipe[k]) and b1[0] == b_pipe[k], k
+        parity.compare(p, scs[402], lin, ang, c_pipe[402], b_pipe[402])
+    finally:
+        s2.close()
