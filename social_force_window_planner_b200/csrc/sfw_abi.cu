@@ -477,6 +477,8 @@ extern "C++" int upload_impl(sfw_ctx *c, const SfwParams *params, const SfwSfmPa
     return fail(c, SFW_ERR_ARG, "sfw_upload: too many samples");
   CK(c, cudaSetDevice(c->device));
   const SfwSfmParams &sfm = sfm_in ? *sfm_in : kDefaultSfm;
+  if (!(sfm.force_sigma_obstacle > 0.0) || !(sfm.gamma > 0.0) || !(sfm.relaxation_time > 0.0))
+    return fail(c, SFW_ERR_ARG, "sfm parameters: force_sigma_obstacle, gamma and relaxation_time must be > 0");
   c->staged = false;
   c->ran = false;
   SfwScratch &X = c->scratch;
