@@ -59,7 +59,9 @@ __device__ __forceinline__ bool wait_for_peers(const unsigned int *arrived, uint
       __nanosleep(200);
       if (global_ns() - t0 > timeout_ns) {
         ok = false;
-        atomicCAS_system(status, 0u, 1u + q);
+        // a plain store: `status` is mapped pinned HOST memory, where device atomics need PCIe atomics support
+        // (compute-sanitizer rejects them); whichever lane's rank lands is a rank that did not deliver
+        *reinterpret_cast<volatile unsigned int *>(status) = 1u + q;
         __threadfence_system();
         break;
       }

@@ -351,7 +351,7 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
         // give up WITHOUT killing the context: this path (and what forks from it) is garbage, the host sees the
         // status word after the stream synchronises and fails the call with SFW_ERR_STATE
         if ((tid & 31u) == 0u) {
-          atomicExch_system(B.status, SFW_DEVSTAT_PATH_WAIT);
+          *reinterpret_cast<volatile unsigned int *>(B.status) = SFW_DEVSTAT_PATH_WAIT; // mapped pinned host word
           __threadfence_system();
         }
         in_range = false;
