@@ -911,6 +911,10 @@ extern "C++" int upload_impl(sfw_ctx *c, const SfwParams *params, const SfwSfmPa
   B.costs = reinterpret_cast<float *>(c->out.dev + c->off_costs);
   B.npts = reinterpret_cast<uint16_t *>(c->out.dev + c->off_npts);
   B.best = reinterpret_cast<SfwBest *>(c->out.dev + c->off_best);
+  // small results (a control tick's cost vector and winner) also land in the pinned host buffer directly
+  c->zero_copy_out = (sizeof(SfwBest) + 4 * (size_t)samples) * n_scenes <= ((size_t)1 << 20);
+  B.costs_host = c->zero_copy_out ? reinterpret_cast<float *>(c->out.host + c->off_costs) : nullptr;
+  B.best_host = c->zero_copy_out ? reinterpret_cast<SfwBest *>(c->out.host + c->off_best) : nullptr;
   B.blockbest = reinterpret_cast<SfwBlockBest *>(c->out.dev + c->off_bb);
   B.counters = reinterpret_cast<unsigned int *>(c->out.dev + c->off_cnt);
   B.map_pitch = map_pitch;
@@ -1620,12 +1624,16 @@ int sfw_download(sfw_ctx *c, float *costs_out, SfwBest *best_out) {
   CK(c, cudaSetDevice(c->device));
   const size_t nb = sizeof(SfwBest) * c->B.n_scenes;
   const size_t nc = 4 * (size_t)c->out_samples * c->B.n_scenes;
-  if (best_out)
-    CK(c, cudaMemcpyAsync(c->out.host + c->off_best, c->out.dev + c->off_best, nb,
-                          cudaMemcpyDeviceToHost, c->stream));
-  if (costs_out)
-    CK(c, cudaMemcpyAsync(c->out.host + c->off_costs, c->out.dev + c->off_costs, nc,
-                          cudaMemcpyDeviceToHost, c->stream));
+  // (a row slab fills the rows outside it on the device only, and an empty slab writes nothing: copy then)
+  const bool landed = c->zero_copy_out && c->B.row_begin == 0 && c->B.row_end == c->B.n_v;
+  if (!landed) {
+    if (best_out)
+      CK(c, cudaMemcpyAsync(c->out.host + c->off_best, c->out.dev + c->off_best, nb,
+                            cudaMemcpyDeviceToHost, c->stream));
+    if (costs_out)
+      CK(c, cudaMemcpyAsync(c->out.host + c->off_costs, c->out.dev + c->off_costs, nc,
+                            cudaMemcpyDeviceToHost, c->stream));
+  }
   CK(c, cudaStreamSynchronize(c->stream));
   if (c->status[0]) { // a kernel gave up (it says why) instead of trapping the context
     const unsigned int code = c->status[0];

@@ -167,6 +167,8 @@ __device__ __forceinline__ void scene_argmin(const SfwBatchDev &B, uint32_t scen
       r.v = r.valid ? B.linvels[bi / n_w] : 0.0;
       r.w = r.valid ? B.angvels[bi % n_w] : 0.0;
       B.best[scene] = r;
+      if (B.best_host)
+        B.best_host[scene] = r;
       if (B.xchg.enabled)
         export_best(B.xchg, scene, r);
     }
@@ -269,6 +271,8 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
     if (!writer && !B.score_zero && v_s == 0.0 && w_s == 0.0) { // sfw_planner.cpp:349-352
       if (tid == 0) {
         B.costs[out] = SFW_COST_SKIPPED;
+        if (B.costs_host)
+          B.costs_host[out] = SFW_COST_SKIPPED;
         B.npts[out] = 0;
       }
       continue;
@@ -822,6 +826,8 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
         cost = (float)c;
       }
       B.costs[out] = cost;
+      if (B.costs_host)
+        B.costs_host[out] = cost;
       B.npts[out] = (uint16_t)npts;
     }
   }

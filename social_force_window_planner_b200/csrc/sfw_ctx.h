@@ -204,6 +204,7 @@ struct sfw_ctx {
   SfwBatchDev B;
   CUtensorMap tmap;
   bool staged = false, ran = false;
+  bool zero_copy_out = false; // the kernels also store costs / winners into out.host (small results)
   // tensor-map cache key
   const void *tm_ptr = nullptr;
   uint32_t tm_pitch = 0, tm_rows = 0, tm_scenes = 0, tm_wp = 0, tm_h = 0;

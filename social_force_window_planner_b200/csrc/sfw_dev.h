@@ -140,6 +140,10 @@ struct SfwBatchDev {
   float *costs;        // [n_scenes][n_v*n_w]
   uint16_t *npts;      // [n_scenes][n_v*n_w] trajectory points recorded before the rollout stopped
   SfwBest *best;       // [n_scenes]
+  // Small results are ALSO stored straight into the pinned host landing buffer (mapped, zero-copy): the stores ride
+  // over PCIe while the kernel runs and sfw_download has nothing left to copy across the bus.  nullptr: off.
+  float *costs_host;
+  SfwBest *best_host;
   SfwBlockBest *blockbest; // [n_scenes][tiles_per_scene]
   unsigned int *counters;  // [n_scenes] tiles finished (self-resetting)
   uint32_t map_pitch, map_rows;

@@ -775,6 +775,8 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
   if (in_range) {
     const size_t o = (size_t)scene * B.n_v * n_w + idx;
     B.costs[o] = cost;
+    if (B.costs_host)
+      B.costs_host[o] = cost;
     B.npts[o] = (uint16_t)npts;
   }
 
@@ -849,6 +851,8 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
         r.v = r.valid ? B.linvels[bi / n_w] : 0.0;
         r.w = r.valid ? B.angvels[bi % n_w] : 0.0;
         B.best[scene] = r;
+        if (B.best_host)
+          B.best_host[scene] = r;
         B.counters[scene] = 0u; // ready for the next launch
         if (B.xchg.enabled)
           export_best(B.xchg, scene, r);
