@@ -385,13 +385,13 @@ def leg_one_scene_per_rank(rig, wl, params, lin, ang, steps, warmup, scene_index
         scene_host = SceneArray([scene])  # the caller's SfwScene structs over its host buffers (built once, like a
         #                                   C++ caller's); every call below still packs + copies them to the device
         with rig.torch.cuda.stream(rig.stream):
-            out = None
+            bufs = None
             for _ in range(3):
-                out = sc.score(params, scene_host, lin, ang, want_costs=True, out=out)
+                bufs = sc.score(params, scene_host, lin, ang, want_costs=True, out=bufs)
             rig.barrier()
             t0 = time.perf_counter()
             for _ in range(steps):  # the caller's output buffers are reused from tick to tick, like its inputs
-                costs_e2e, best_e2e = out = sc.score(params, scene_host, lin, ang, want_costs=True, out=out)
+                costs_e2e, best_e2e = bufs = sc.score(params, scene_host, lin, ang, want_costs=True, out=bufs)
                 if fused:
                     sc.exchange_sync()
                     sc.sync()
@@ -435,13 +435,13 @@ def leg_c3(rig, steps, warmup):
             ok = ok and bool(np.array_equal(got, rig.nccl_gather_best(sc, e - b)))
         verified = bool(rig.reduce([1.0 if ok else 0.0], "min")[0] == 1.0)
     with rig.torch.cuda.stream(rig.stream):
-        out = None
+        bufs = None
         for _ in range(2):
-            out = sc.score(params, scenes, lin, ang, want_costs=True, out=out)
+            bufs = sc.score(params, scenes, lin, ang, want_costs=True, out=bufs)
         rig.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
-            costs_e2e, best_e2e = out = sc.score(params, scenes, lin, ang, want_costs=True, out=out)
+            costs_e2e, best_e2e = bufs = sc.score(params, scenes, lin, ang, want_costs=True, out=bufs)
             if fused:
                 sc.exchange_sync()
                 sc.sync()
