@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 #include "sfw_dev.h"
 #include "sfw_kernels.h"
@@ -558,12 +559,13 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
       for (uint32_t m = 0; m < owned; ++m) {
         const uint32_t a = tid + m * kCrowdThreads;
         const bool act = a < P2;
-        float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), va = pa;
+        // Lanes past the last pair (the tail of the last warp) walk the ring as pair 0 and never store: the loop
+        // below then has no divergent region at all — one basic block per cyclic offset.
+        const uint32_t ar = act ? a : 0u;
+        const float4 pa = sm.pos[ar], va = sm.vel[ar];
         f2 FX = bc2(0.f), FY = bc2(0.f);
         f2 s0x = bc2(0.f), s0y = bc2(0.f), s1x = bc2(0.f), s1y = bc2(0.f);
         if (act) {
-          pa = sm.pos[a];
-          va = sm.vel[a];
           f2 fx, fy, fm;
           pair_force2<true>(K, mk2(pa.x, pa.y), mk2(pa.z, pa.w), mk2(va.x, va.y), mk2(va.z, va.w), RX, RY, RVX,
                             RVY, fx, fy, fm);
@@ -579,30 +581,59 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
         }
         const f2 A0X = bc2(pa.x), A0Y = bc2(pa.z), A0VX = bc2(va.x), A0VY = bc2(va.z);
         const f2 A1X = bc2(pa.y), A1Y = bc2(pa.w), A1VX = bc2(va.y), A1VY = bc2(va.w);
-        const uint32_t n_off = half + (even ? 1u : 0u);
-        for (uint32_t off = 1; off <= n_off; ++off) {
-          const bool go = act && (off <= half || a < P2 / 2u);
-          if (go) {
-            uint32_t j = a + off;
-            if (j >= P2)
-              j -= P2;
-            const float4 pb = sm.pos[j], vb = sm.vel[j];
-            const f2 BX = mk2(pb.x, pb.y), BY = mk2(pb.z, pb.w);
-            const f2 BVX = mk2(vb.x, vb.y), BVY = mk2(vb.z, vb.w);
-            f2 hx, hy, gx2, gy2, hm;
-            pair_force2<false>(K, A0X, A0Y, A0VX, A0VY, BX, BY, BVX, BVY, hx, hy, hm);
-            pair_force2<false>(K, A1X, A1Y, A1VX, A1VY, BX, BY, BVX, BVY, gx2, gy2, hm);
-            s0x = add2(s0x, hx);
-            s0y = add2(s0y, hy);
-            s1x = add2(s1x, gx2);
-            s1y = add2(s1y, gy2);
-            const float4 fb4 = myrow[j];
-            float bx0, bx1, by0, by1;
-            un2(sub2(mk2(fb4.x, fb4.y), add2(hx, gx2)), bx0, bx1);
-            un2(sub2(mk2(fb4.z, fb4.w), add2(hy, gy2)), by0, by1);
+        // one cyclic offset: pair a against pair j (state already in registers), reaction pushed into the warp's row
+        // GATED: lanes with `push` false leave no trace (the opposite-pair trip, once per step); otherwise every
+        // lane runs the same instructions and only the store of the lanes past the last pair is predicated off
+        // (they read their "row entry" from a location nobody writes in this phase).
+        auto trip = [&](const float4 pb, const float4 vb, const uint32_t j, const bool push, auto gated) {
+          constexpr bool GATED = decltype(gated)::value;
+          if (GATED && !push)
+            return;
+          const float4 *src = (GATED || push) ? myrow + j : sm.pos;
+          const float4 fb4 = *src; // within one offset the lanes hit distinct entries
+          const f2 BX = mk2(pb.x, pb.y), BY = mk2(pb.z, pb.w);
+          const f2 BVX = mk2(vb.x, vb.y), BVY = mk2(vb.z, vb.w);
+          f2 hx, hy, gx2, gy2, hm;
+          pair_force2<false>(K, A0X, A0Y, A0VX, A0VY, BX, BY, BVX, BVY, hx, hy, hm);
+          pair_force2<false>(K, A1X, A1Y, A1VX, A1VY, BX, BY, BVX, BVY, gx2, gy2, hm);
+          s0x = add2(s0x, hx);
+          s0y = add2(s0y, hy);
+          s1x = add2(s1x, gx2);
+          s1y = add2(s1y, gy2);
+          float bx0, bx1, by0, by1;
+          un2(sub2(mk2(fb4.x, fb4.y), add2(hx, gx2)), bx0, bx1);
+          un2(sub2(mk2(fb4.z, fb4.w), add2(hy, gy2)), by0, by1);
+          if (push)
             myrow[j] = make_float4(bx0, bx1, by0, by1);
+        };
+        // The ring is walked with the NEXT pair's state fetched one offset ahead: the reaction push of an offset
+        // (a shared-memory read-modify-write the compiler must keep in order with every other shared access) would
+        // otherwise put the load latency of pos / vel at the head of every trip.
+        // (a warp with no pair at all — small crowds leave most of the block without one — skips the walk: its
+        // lanes would only take issue slots from the warps that own pairs)
+        const bool warp_owns = __any_sync(0xffffffffu, act); // a vote: the compiler sees a uniform branch
+        uint32_t j = ar + 1u;
+        if (j >= P2)
+          j -= P2;
+        float4 pb = make_float4(0.f, 0.f, 0.f, 0.f), vb = pb;
+        if (warp_owns) {
+          pb = sm.pos[j];
+          vb = sm.vel[j];
+          for (uint32_t off = 1; off <= half; ++off) {
+            uint32_t jn = j + 1u;
+            if (jn >= P2)
+              jn -= P2;
+            const float4 pbn = sm.pos[jn], vbn = sm.vel[jn];
+            trip(pb, vb, j, act, std::false_type{});
+            __syncwarp(); // lane t+1's push to entry j lands before lane t reaches it one offset later
+            j = jn;
+            pb = pbn;
+            vb = vbn;
           }
-          __syncwarp(); // lane t+1's push to entry j lands before lane t reaches it one offset later
+        }
+        if (even) { // the opposite pair of the ring: first half of the ring only
+          trip(pb, vb, j, act && a < P2 / 2u, std::true_type{});
+          __syncwarp();
         }
         if (act) {
           float l0, h0, l1, h1;

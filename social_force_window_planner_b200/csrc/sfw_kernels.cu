@@ -42,6 +42,10 @@
 
 #include "sfw_forces.cuh"
 
+#ifndef SFW_SMALL_PREFETCH
+#define SFW_SMALL_PREFETCH 1
+#endif
+
 // ================================================================================================
 // Kernel: one thread per trajectory
 // ================================================================================================
@@ -597,8 +601,19 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
           const f2 A0X = bc2(pa.x), A0Y = bc2(pa.z), A0VX = bc2(va.x), A0VY = bc2(va.z);
           const f2 A1X = bc2(pa.y), A1Y = bc2(pa.w), A1VX = bc2(va.y), A1VY = bc2(va.w);
           f2 s0x = bc2(0.f), s0y = bc2(0.f), s1x = bc2(0.f), s1y = bc2(0.f);
+#if SFW_SMALL_PREFETCH
+          // the next pair's state is fetched one trip ahead: the reaction push at the end of a trip is a shared-memory
+          // store the compiler must keep in order with every later shared load, which would put the load latency of
+          // pos / vel at the head of every trip
+          // (one array past the last pair on the final trip: pos runs into vel, vel into frc — in bounds, unused)
+          uint32_t o = (k + 1u) * T;
+          float4 pb = pos[o], vb = vel[o];
+          for (uint32_t j = k + 1; j < P2; ++j, o += T) {
+            const float4 pbn = pos[o + T], vbn = vel[o + T];
+#else
           for (uint32_t j = k + 1; j < P2; ++j) {
             const float4 pb = pos[j * T], vb = vel[j * T];
+#endif
             const f2 BX = mk2(pb.x, pb.y), BY = mk2(pb.z, pb.w);
             const f2 BVX = mk2(vb.x, vb.y), BVY = mk2(vb.z, vb.w);
             f2 hx, hy, gx2, gy2, hm;
@@ -608,11 +623,20 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
             s0y = add2(s0y, hy);
             s1x = add2(s1x, gx2);
             s1y = add2(s1y, gy2);
-            const float4 fb4 = frc[j * T];
+#if SFW_SMALL_PREFETCH
+            float4 *fb = frc + o;
+#else
+            float4 *fb = frc + j * T;
+#endif
+            const float4 fb4 = *fb;
             float bx0, bx1, by0, by1;
             un2(sub2(mk2(fb4.x, fb4.y), add2(hx, gx2)), bx0, bx1);
             un2(sub2(mk2(fb4.z, fb4.w), add2(hy, gy2)), by0, by1);
-            frc[j * T] = make_float4(bx0, bx1, by0, by1);
+            *fb = make_float4(bx0, bx1, by0, by1);
+#if SFW_SMALL_PREFETCH
+            pb = pbn;
+            vb = vbn;
+#endif
           }
           {
             float l0, h0, l1, h1;
