@@ -475,6 +475,21 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
         }
         __syncwarp();
       }
+      // the robot's sums of this warp (its own social force, the pedestrians' social work terms) -> sm.red
+      auto reduce_robot_sums = [&]() {
+        float l, h;
+        un2(rfx2, l, h);
+        const float rfx = warp_sum(l + h);
+        un2(rfy2, l, h);
+        const float rfy = warp_sum(l + h);
+        un2(wp2, l, h);
+        const float wp = warp_sum(l + h);
+        if (lane == 0) {
+          sm.red[warp * 4 + 0] = rfx;
+          sm.red[warp * 4 + 1] = rfy;
+          sm.red[warp * 4 + 2] = wp;
+        }
+      };
       // -- phase 1: forces (sfw_planner.cpp:592) --
       if (spread) {
         const uint32_t a = lane;
@@ -555,7 +570,33 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
           un2(add2(mk2(own.z, own.w), FY), y0, y1);
           myrow[a] = make_float4(x0, x1, y0, y1);
         }
-      } else
+        reduce_robot_sums();
+      } else {
+      // pass A: every owned pair against the robot and inside itself, added to the pair's own row entry; the robot's
+      // sums leave the registers before the ring walk (the walk runs at the register limit: ten live registers
+      // fewer let the compiler keep its loop-carried sums in place)
+      for (uint32_t m = 0; m < owned; ++m) {
+        const uint32_t a = tid + m * kCrowdThreads;
+        if (a < P2) {
+          const float4 pa = sm.pos[a], va = sm.vel[a];
+          f2 fx, fy, fm;
+          pair_force2<true>(K, mk2(pa.x, pa.y), mk2(pa.z, pa.w), mk2(va.x, va.y), mk2(va.z, va.w), RX, RY, RVX,
+                            RVY, fx, fy, fm);
+          rfx2 = sub2(rfx2, fx);
+          rfy2 = sub2(rfy2, fy);
+          wp2 = add2(wp2, fm);
+          float gx_, gy_, gm_;
+          pair_force<false>(K, pa.x, pa.z, va.x, va.z, pa.y, pa.w, va.y, va.w, gx_, gy_, gm_);
+          const float4 own = myrow[a];
+          float x0, x1, y0, y1;
+          un2(add2(mk2(own.x, own.y), add2(fx, mk2(gx_, -gx_))), x0, x1);
+          un2(add2(mk2(own.z, own.w), add2(fy, mk2(gy_, -gy_))), y0, y1);
+          myrow[a] = make_float4(x0, x1, y0, y1);
+        }
+      }
+      reduce_robot_sums();
+      __syncwarp();
+      // pass B: the cyclic cross-pair walk
       for (uint32_t m = 0; m < owned; ++m) {
         const uint32_t a = tid + m * kCrowdThreads;
         const bool act = a < P2;
@@ -563,22 +604,7 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
         // below then has no divergent region at all — one basic block per cyclic offset.
         const uint32_t ar = act ? a : 0u;
         const float4 pa = sm.pos[ar], va = sm.vel[ar];
-        f2 FX = bc2(0.f), FY = bc2(0.f);
         f2 s0x = bc2(0.f), s0y = bc2(0.f), s1x = bc2(0.f), s1y = bc2(0.f);
-        if (act) {
-          f2 fx, fy, fm;
-          pair_force2<true>(K, mk2(pa.x, pa.y), mk2(pa.z, pa.w), mk2(va.x, va.y), mk2(va.z, va.w), RX, RY, RVX,
-                            RVY, fx, fy, fm);
-          FX = fx;
-          FY = fy;
-          rfx2 = sub2(rfx2, fx);
-          rfy2 = sub2(rfy2, fy);
-          wp2 = add2(wp2, fm);
-          float gx_, gy_, gm_;
-          pair_force<false>(K, pa.x, pa.z, va.x, va.z, pa.y, pa.w, va.y, va.w, gx_, gy_, gm_);
-          FX = add2(FX, mk2(gx_, -gx_));
-          FY = add2(FY, mk2(gy_, -gy_));
-        }
         const f2 A0X = bc2(pa.x), A0Y = bc2(pa.z), A0VX = bc2(va.x), A0VY = bc2(va.z);
         const f2 A1X = bc2(pa.y), A1Y = bc2(pa.w), A1VX = bc2(va.y), A1VY = bc2(va.w);
         // one cyclic offset: pair a against pair j (state already in registers), reaction pushed into the warp's row
@@ -639,10 +665,10 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
           float l0, h0, l1, h1;
           un2(s0x, l0, h0);
           un2(s1x, l1, h1);
-          FX = add2(FX, mk2(l0 + h0, l1 + h1));
+          f2 FX = mk2(l0 + h0, l1 + h1);
           un2(s0y, l0, h0);
           un2(s1y, l1, h1);
-          FY = add2(FY, mk2(l0 + h0, l1 + h1));
+          f2 FY = mk2(l0 + h0, l1 + h1);
           if (!n_help) {
             f2 ox, oy;
             obstacle_sum2(sm.obs, (int)M, B.c_obs, mk2(pa.x, pa.y), mk2(pa.z, pa.w), ox, oy);
@@ -658,6 +684,7 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
           myrow[a] = make_float4(x0, x1, y0, y1);
         }
         __syncwarp();
+      }
       }
       if (help_idx >= 1u && help_idx <= n_help && help_pair < P2 && M) {
         const float4 pa = sm.pos[help_pair];
@@ -678,20 +705,6 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
         if (lane == 0u) {
           sm.red[3] = rox * a_obs_scale;
           sm.red[7] = roy * a_obs_scale;
-        }
-      }
-      {
-        float l, h;
-        un2(rfx2, l, h);
-        const float rfx = warp_sum(l + h);
-        un2(rfy2, l, h);
-        const float rfy = warp_sum(l + h);
-        un2(wp2, l, h);
-        const float wp = warp_sum(l + h);
-        if (lane == 0) {
-          sm.red[warp * 4 + 0] = rfx;
-          sm.red[warp * 4 + 1] = rfy;
-          sm.red[warp * 4 + 2] = wp;
         }
       }
       __syncthreads();
