@@ -29,6 +29,10 @@ namespace {
 
 constexpr int kCrowdThreads = SFW_CROWD_THREADS;
 constexpr int kCrowdWarps = kCrowdThreads / 32;
+// The thread that carries a trajectory's social work: lane 0 of warp 1.  Warp 0 integrates the pairs of a small
+// crowd in phase 2; the robot's terms are reduced beside it, not after it (one warp alone runs a dependent chain at
+// 7+ cycles per instruction: a 5 x 9 tick is nothing but such chains).
+constexpr uint32_t kWorkWarp = 1u, kWorkTid = 32u * kWorkWarp;
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -405,7 +409,7 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
     const double base_x = scp->rx, base_y = scp->ry;
     const float rr2 = B.rr2;
     const float a_obs_scale = scp->a_obs_scale;
-    double social_work = 0.0; // thread 0 only
+    double social_work = 0.0; // thread kWorkTid only
     const uint32_t half = P2 ? (P2 - 1u) / 2u : 0u; // full cyclic offsets
     const bool even = P2 >= 2u && (P2 & 1u) == 0u; // + the opposite pair, first half of the ring only
     const uint32_t owned = (P2 + kCrowdThreads - 1u) / kCrowdThreads;
@@ -448,7 +452,6 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
       const float pry = (i == 0) ? scp->ay : (float)(sm.ry[i] - base_y);
       const float rvxf = (i == 0) ? scp->avx : sm.rvx[i];
       const float rvyf = (i == 0) ? scp->avy : (float)vy;
-      const float nrx = (float)(sm.rx[i + 1] - base_x), nry = (float)(sm.ry[i + 1] - base_y);
       const f2 RX = bc2(prx), RY = bc2(pry), RVX = bc2(rvxf), RVY = bc2(rvyf);
       f2 rfx2 = bc2(0.f), rfy2 = bc2(0.f), wp2 = bc2(0.f);
 
@@ -570,7 +573,10 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
           un2(add2(mk2(own.z, own.w), FY), y0, y1);
           myrow[a] = make_float4(x0, x1, y0, y1);
         }
-        reduce_robot_sums();
+        if (warp == 0u) // the only warp that met the robot in this layout
+          reduce_robot_sums();
+        else if (lane < 3u)
+          sm.red[warp * 4 + lane] = 0.f;
       } else {
       // pass A: every owned pair against the robot and inside itself, added to the pair's own row entry; the robot's
       // sums leave the registers before the ring walk (the walk runs at the register limit: ten live registers
@@ -701,7 +707,8 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
       if (warp == (uint32_t)kCrowdWarps - 1u) { // the robot's obstacle force: off the critical path of phase 2
         __syncwarp();
         float rox, roy;
-        robot_obstacle_sum_warp(sm.obs, M, B.c_obs, prx, pry, lane, rox, roy);
+        const float qrx = (i == 0) ? scp->ax : (float)(sm.rx[i] - base_x), qry = (i == 0) ? scp->ay : (float)(sm.ry[i] - base_y);
+        robot_obstacle_sum_warp(sm.obs, M, B.c_obs, qrx, qry, lane, rox, roy);
         if (lane == 0u) {
           sm.red[3] = rox * a_obs_scale;
           sm.red[7] = roy * a_obs_scale;
@@ -712,16 +719,28 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
       // -- phase 2: updatePosition (:594), collision (:613-627), social work (:629) --
       bool hit = false;
       const f2 DT = bc2(dtf);
+      // (computed here, not at the top of the step: nothing that the ring walk does not need stays live across it)
+      const float nrx = (float)(sm.rx[i + 1] - base_x), nry = (float)(sm.ry[i + 1] - base_y);
       for (uint32_t m = 0; m < owned; ++m) {
         const uint32_t a = tid + m * kCrowdThreads;
         if (a >= P2)
           break;
+        // One warp alone walks this chain in a small crowd, so its length is the step's: all rows are loaded before
+        // the first is cleared (a store between two loads pins their order), and — lanes are different PEDESTRIANS
+        // here — the conditional rsqrt / goal-flag updates are selects, so that no data-dependent branch can split
+        // the warp.
         f2 FX = bc2(0.f), FY = bc2(0.f);
-        for (uint32_t w = 0; w < (uint32_t)kCrowdWarps; ++w) {
-          const float4 f = sm.frc[w * P2 + a];
-          FX = add2(FX, mk2(f.x, f.y));
-          FY = add2(FY, mk2(f.z, f.w));
-          sm.frc[w * P2 + a] = make_float4(0.f, 0.f, 0.f, 0.f);
+        {
+          float4 f[kCrowdWarps];
+#pragma unroll
+          for (uint32_t w = 0; w < (uint32_t)kCrowdWarps; ++w)
+            f[w] = sm.frc[w * P2 + a];
+#pragma unroll
+          for (uint32_t w = 0; w < (uint32_t)kCrowdWarps; ++w) {
+            FX = add2(FX, mk2(f[w].x, f[w].y));
+            FY = add2(FY, mk2(f[w].z, f[w].w));
+            sm.frc[w * P2 + a] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
         const float4 pa = sm.pos[a], va = sm.vel[a];
         const f2 AX = mk2(pa.x, pa.y), AY = mk2(pa.z, pa.w), AVX = mk2(va.x, va.y), AVY = mk2(va.z, va.w);
@@ -731,14 +750,16 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
         un2(fma2(gdx, gdx, mul2(gdy, gdy)), g20, g21);
         const bool hg0 = sm.goalflag[2 * a] != 0, hg1 = sm.goalflag[2 * a + 1] != 0;
         const bool go0 = hg0 && g20 > Pp.x, go1 = hg1 && g21 > Pp.y;
-        const f2 gs = mk2(go0 ? rsqrt_approx(g20) * Pp.z : 0.f, go1 ? rsqrt_approx(g21) * Pp.w : 0.f);
+        const float rg0 = rsqrt_approx(g20) * Pp.z, rg1 = rsqrt_approx(g21) * Pp.w; // (inf / NaN at g2 == 0: not selected)
+        const f2 gs = mk2(go0 ? rg0 : 0.f, go1 ? rg1 : 0.f);
         const f2 c1 = mk2(go0 ? B.kd_tau : B.inv_tau, go1 ? B.kd_tau : B.inv_tau);
         const f2 Fx = add2(mul2(c1, sub2(mul2(gdx, gs), AVX)), FX);
         const f2 Fy = add2(mul2(c1, sub2(mul2(gdy, gs), AVY)), FY);
         f2 nvx = fma2(Fx, DT, AVX), nvy = fma2(Fy, DT, AVY);
         float v20, v21;
         un2(fma2(nvx, nvx, mul2(nvy, nvy)), v20, v21);
-        const f2 sc = mk2(v20 > Pc.z ? Pp.z * rsqrt_approx(v20) : 1.0f, v21 > Pc.w ? Pp.w * rsqrt_approx(v21) : 1.0f);
+        const float rs0 = Pp.z * rsqrt_approx(v20), rs1 = Pp.w * rsqrt_approx(v21);
+        const f2 sc = mk2(v20 > Pc.z ? rs0 : 1.0f, v21 > Pc.w ? rs1 : 1.0f);
         nvx = mul2(nvx, sc);
         nvy = mul2(nvy, sc);
         const f2 npx = fma2(nvx, DT, AX), npy = fma2(nvy, DT, AY);
@@ -753,10 +774,9 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
           const f2 hx = sub2(mk2(G.x, G.y), npx), hy = sub2(mk2(G.z, G.w), npy);
           float h0, h1;
           un2(fma2(hx, hx, mul2(hy, hy)), h0, h1);
-          if (hg0 && h0 <= Pp.x)
-            sm.goalflag[2 * a] = 0;
-          if (hg1 && h1 <= Pp.y)
-            sm.goalflag[2 * a + 1] = 0;
+          // goal reached -> pop: both flags of the pair in one 16-bit store, whatever they turn out to be
+          const uint32_t f0 = (hg0 && !(h0 <= Pp.x)) ? 1u : 0u, f1 = (hg1 && !(h1 <= Pp.y)) ? 1u : 0u;
+          *reinterpret_cast<uint16_t *>(sm.goalflag + 2 * a) = (uint16_t)(f0 | (f1 << 8));
         }
         {
           const f2 cx = sub2(bc2(nrx), npx), cy = sub2(bc2(nry), npy);
@@ -767,7 +787,7 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
       }
       if (hit)
         sm.flags[1] = 1;
-      if (warp == 0) { // robot terms: wr from the forces of :592, wp belongs to the previous step
+      if (warp == kWorkWarp) { // robot terms: wr from the forces of :592, wp belongs to the previous step
         float rfx = (lane < (uint32_t)kCrowdWarps) ? sm.red[lane * 4 + 0] : 0.f;
         float rfy = (lane < (uint32_t)kCrowdWarps) ? sm.red[lane * 4 + 1] : 0.f;
         float wp = (lane < (uint32_t)kCrowdWarps) ? sm.red[lane * 4 + 2] : 0.f;
@@ -796,7 +816,7 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
           gf[2 * k] = sm.goalflag[2 * k];
           gf[2 * k + 1] = sm.goalflag[2 * k + 1];
         }
-        if (tid == 0) {
+        if (tid == kWorkTid) {
           *reinterpret_cast<double *>(rec) = social_work;
           reinterpret_cast<int *>(rec)[2] = 1;
           reinterpret_cast<int *>(rec)[3] = i + 1;
@@ -807,7 +827,7 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
     if (writer) {
       // step counts the path did not reach alive: a collision kills every descendant; an illegal pose is seen
       // by the descendants' own footprint check (same poses), they only must not read a stale record
-      if (tid == 0)
+      if (tid == kWorkTid)
         for (int k = written + 1; k <= (int)B.share.kmax; ++k) {
           uint8_t *rec = rec_out + (size_t)k * B.share.rec_bytes;
           *reinterpret_cast<double *>(rec) = social_work;
@@ -838,7 +858,7 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
         sm.red[warp * 4 + 3] = wp;
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == kWorkTid) {
       float cost = SFW_COST_INVALID;
       // points recorded: one per legal pose until the first violation (sfw_planner.cpp:578)
       int npts = collided ? steps_done : (S_eff < S ? S_eff : S);
@@ -851,9 +871,10 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
         for (int i = 0; i < S; ++i)
           costmap_sum = __dadd_rn(costmap_sum, __ddiv_rn((double)sm.fcm[i], 255.0));
         const double x = sm.rx[S], y = sm.ry[S], th = sm.rth[S];
+        const double v_end = B.linvels[idx / n_w]; // (a sample, not a shared path: reloaded, not kept live)
         double vx = scp->rvx;
         for (int i = 0; i < S; ++i)
-          vx = step_velocity(v_s, vx, ax_dt);
+          vx = step_velocity(v_end, vx, ax_dt);
         const double dx = __dsub_rn(scp->wpx, x), dy = __dsub_rn(scp->wpy, y);
         const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
         const double dtheta = atan2(dy, dx);
