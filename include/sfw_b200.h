@@ -342,6 +342,9 @@ uint64_t sfw_h2d_bytes(const sfw_ctx *ctx);
 uint64_t sfw_d2h_bytes(const sfw_ctx *ctx);
 /* name of the kernel variant the last sfw_run dispatched to (for logs/profiles) */
 const char *sfw_last_kernel(const sfw_ctx *ctx);
+/* threads per block of the plan of the staged batch (the thread-per-trajectory kernel's tile, or the block size of the
+ * block-per-trajectory kernel: 256, or 128 for a small crowd on a grid where that saves a wave); 0 before sfw_upload */
+uint32_t sfw_block_threads(const sfw_ctx *ctx);
 /* rollout prefix sharing of the staged batch: mean number of leading steps a sample takes from a shared path
  * instead of simulating them itself (0 when sharing is off for this batch) */
 double sfw_shared_prefix_steps(const sfw_ctx *ctx);

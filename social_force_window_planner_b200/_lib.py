@@ -19,7 +19,7 @@ EXPORTS = [
     "sfw_default_sfm_params", "sfw_score", "sfw_score_batch", "sfw_upload", "sfw_run",
     "sfw_download", "sfw_sync", "sfw_set_row_slab", "sfw_trajectory_points", "sfw_stream",
     "sfw_device_costs", "sfw_device_best", "sfw_kernel_launches", "sfw_algorithmic_bytes",
-    "sfw_last_kernel", "sfw_shared_prefix_steps", "sfw_h2d_bytes", "sfw_d2h_bytes", "sfw_laser_obstacles", "sfw_marker_points", "sfw_exchange_export", "sfw_exchange_connect",
+    "sfw_last_kernel", "sfw_block_threads", "sfw_shared_prefix_steps", "sfw_h2d_bytes", "sfw_d2h_bytes", "sfw_laser_obstacles", "sfw_marker_points", "sfw_exchange_export", "sfw_exchange_connect",
     "sfw_exchange_sync", "sfw_exchange_fetch", "sfw_exchange_device_buffer", "sfw_exchange_expect", "sfw_exchange_connect_local", "sfw_set_zero_sample", "sfw_set_host_threads",
     "sfw_exchange_set_timeout", "sfw_exchange_merge", "sfw_exchange_merged_device", "sfw_set_policy", "sfw_set_prefix_sharing", "sfw_may_i_stop",
     "sfw_set_obstacle_cutoff", "sfw_obstacle_skip_fraction", "sfw_obstacle_layout",
@@ -76,6 +76,8 @@ def load() -> C.CDLL:
     lib.sfw_kernel_launches.argtypes = [_ctx]
     lib.sfw_algorithmic_bytes.restype = C.c_uint64
     lib.sfw_algorithmic_bytes.argtypes = [_ctx]
+    lib.sfw_block_threads.restype = C.c_uint32
+    lib.sfw_block_threads.argtypes = [_ctx]
     for f in (lib.sfw_h2d_bytes, lib.sfw_d2h_bytes):
         f.restype = C.c_uint64
         f.argtypes = [_ctx]

@@ -122,9 +122,11 @@ int run_launch(sfw_ctx *c, const RunState &rs, uint32_t s0, uint32_t cnt);
 // SM under the shared-memory and register limits, then shrink the block so a single-wave launch
 // is spread evenly over all SMs.
 // family: -1 = choose the kernel family here; 0 / 1 = keep thread-per-trajectory / block-per-trajectory (a row
-// slab must be scored by the kernel its full grid was planned for, so that sharding never changes a bit).
+// slab must be scored by the kernel its full grid was planned for, so that sharding never changes a bit);
+// crowd_threads: likewise the block size of the block-per-trajectory kernel (its two instantiations sum the
+// per-warp accumulator rows in different groupings), 0 = choose.
 int make_plan(sfw_ctx *c, uint32_t n_scenes, uint32_t samples, uint32_t P, uint32_t M, uint32_t F,
-              uint32_t win_wp, uint32_t win_h, int steps, int family = -1) {
+              uint32_t win_wp, uint32_t win_h, int steps, int family = -1, uint32_t crowd_threads = 0) {
   Plan &pl = c->plan;
   if (pl.valid && pl.n_scenes == n_scenes && pl.samples == samples && pl.maxP == P && pl.maxM == M &&
       pl.maxF == F && pl.win_wp == win_wp && pl.win_h == win_h && pl.steps == steps)
@@ -140,7 +142,38 @@ int make_plan(sfw_ctx *c, uint32_t n_scenes, uint32_t samples, uint32_t P, uint3
     try_small = false; // fewer than 4 warps per SM would fit
   if (family == 1 || (family < 0 && c->policy == SFW_POLICY_LATENCY))
     try_small = false;
-  const size_t crowd_smem = sfw_crowd_smem_bytes(P, M, F, (uint32_t)steps);
+  // Block-per-trajectory kernel: 256-thread blocks (two per SM), or — a small crowd on a grid of a few waves —
+  // 128-thread blocks (four per SM) when that saves waves.  Measured end to end on one wave of 5 x 9 samples
+  // (scripts/lat_variants.sh): a 128-thread block is 1.06 - 1.09 x slower per trajectory up to 5 pedestrians and
+  // 1.25 - 1.32 x at 20 - 40; BASELINE's 21 x 21 / 5-pedestrian tick goes from two waves to one: 0.100 -> 0.066 ms.
+  uint32_t crowd_T = crowd_threads ? crowd_threads : (uint32_t)SFW_CROWD_THREADS;
+  size_t crowd_smem = sfw_crowd_smem_bytes(P, M, F, (uint32_t)steps, crowd_T);
+  int crowd_k = 0;
+  double crowd_waves = 0.0; // waves of the chosen block size, in units of a 256-thread wave's time
+  const uint64_t crowd_total = (uint64_t)n_scenes * samples;
+  if (crowd_smem <= max_dyn) {
+    CK(c, sfw_crowd_prepare(crowd_T, crowd_smem, &crowd_k));
+    if (crowd_k > 0) {
+      const uint64_t slots = (uint64_t)c->sm_count * crowd_k;
+      const uint64_t waves = (crowd_total + slots - 1) / slots;
+      crowd_waves = (double)waves;
+      if (!crowd_threads && P <= SFW_MAX_PEDS_SMALL && waves >= 2 && waves <= 8) {
+        const size_t smem_s = sfw_crowd_smem_bytes(P, M, F, (uint32_t)steps, SFW_CROWD_THREADS_SMALL);
+        int k_s = 0;
+        CK(c, sfw_crowd_prepare(SFW_CROWD_THREADS_SMALL, smem_s, &k_s));
+        if (k_s > 0) {
+          const uint64_t slots_s = (uint64_t)c->sm_count * k_s;
+          const double waves_s = (double)((crowd_total + slots_s - 1) / slots_s) * (P <= 6 ? 1.1 : 1.3);
+          if (waves_s < crowd_waves) {
+            crowd_T = SFW_CROWD_THREADS_SMALL;
+            crowd_smem = smem_s;
+            crowd_k = k_s;
+            crowd_waves = waves_s;
+          }
+        }
+      }
+    }
+  }
   if (try_small && family < 0 && c->policy == SFW_POLICY_AUTO && crowd_smem <= max_dyn) {
     // Small grids are latency bound in the thread-per-trajectory kernel: one thread walks every pair of a
     // trajectory, so a tick costs what ONE warp costs however few trajectories there are.  The block-per-trajectory
@@ -149,27 +182,22 @@ int make_plan(sfw_ctx *c, uint32_t n_scenes, uint32_t samples, uint32_t P, uint3
     // 0 ... 40 pedestrians): thread per trajectory 2.1 + 0.63 P + 0.016 P^2 us, block per trajectory
     // 1.65 + 0.085 P us per WAVE of blocks.  A single wave always wins (116 vs 135 us without pedestrians,
     // 132 vs 188 us with one, 40 steps); two waves from 3 pedestrians on; at 20 pedestrians up to 8 waves.
-    int k = 0;
-    CK(c, sfw_crowd_prepare(crowd_smem, &k));
-    if (k > 0) {
-      const uint64_t total = (uint64_t)n_scenes * samples;
-      const uint64_t waves = (total + (uint64_t)c->sm_count * k - 1) / ((uint64_t)c->sm_count * k);
+    if (crowd_k > 0) {
       const double Pd = (double)P;
       // (from 4 pedestrian pairs on the block-per-trajectory kernel spreads its force phase over all warps:
       // 2.0 + 0.027 P us per step and wave, 155 us end to end at 20 pedestrians, 170 us at 40)
       const double wave_us = P >= 7 ? 2.0 + 0.027 * Pd : 1.65 + 0.085 * Pd;
-      if ((double)waves * wave_us < 2.1 + 0.63 * Pd + 0.016 * Pd * Pd)
+      if (crowd_waves * wave_us < 2.1 + 0.63 * Pd + 0.016 * Pd * Pd)
         try_small = false;
     }
   }
   if (!try_small) {
     const size_t smem = crowd_smem;
-    int k = 0;
+    const int k = crowd_k;
     if (smem > max_dyn)
       return fail(c, SFW_ERR_UNSUPPORTED,
                   "scene does not fit the block-per-trajectory kernel (peds=%u steps=%d: %zu B of shared memory)",
                   P, steps, smem);
-    CK(c, sfw_crowd_prepare(smem, &k));
     if (k <= 0)
       return fail(c, SFW_ERR_UNSUPPORTED, "block-per-trajectory kernel cannot be resident (peds=%u)", P);
     const uint64_t total = (uint64_t)n_scenes * samples;
@@ -183,7 +211,7 @@ int make_plan(sfw_ctx *c, uint32_t n_scenes, uint32_t samples, uint32_t P, uint3
     pl.steps = steps;
     pl.crowd = true;
     pl.grid = (uint32_t)std::min<uint64_t>(total, (uint64_t)c->sm_count * k);
-    pl.T = SFW_CROWD_THREADS;
+    pl.T = crowd_T;
     pl.tiles = 1;
     pl.smem = smem;
     pl.valid = true;
@@ -1414,7 +1442,7 @@ int run_prepare(sfw_ctx *c, RunState &rs) {
     Plan saved = c->plan;
     c->plan.valid = false;
     int rc = make_plan(c, B.n_scenes, std::max(samples, 1u), saved.maxP, saved.maxM, saved.maxF,
-                       saved.win_wp, saved.win_h, saved.steps, saved.crowd ? 1 : 0);
+                       saved.win_wp, saved.win_h, saved.steps, saved.crowd ? 1 : 0, saved.crowd ? saved.T : 0u);
     if (rc != SFW_OK)
       return rc;
     B.tiles_per_scene = c->plan.tiles;
@@ -1508,14 +1536,14 @@ int run_launch(sfw_ctx *c, const RunState &rs, uint32_t s0, uint32_t cnt) {
     for (uint32_t mode = 1; mode <= 3; ++mode) {
       W.share.mode = mode;
       const uint64_t items = (uint64_t)B.n_scenes * (mode == 1 ? 4u : mode == 2 ? c->share_paths - 4u : c->out_samples);
-      CK(c, sfw_launch_crowd(W, wc, (uint32_t)std::min<uint64_t>(items, c->plan.grid), c->plan.smem, c->stream, mode == 3));
+      CK(c, sfw_launch_crowd(W, wc, (uint32_t)std::min<uint64_t>(items, c->plan.grid), c->plan.T, c->plan.smem, c->stream, mode == 3));
     }
     c->launches += sfw_crowd_fuses_argmin(W) ? 3 : 4;
     c->last_kernel = "sfw_score_crowd,share";
   } else if (re > rb && c->plan.crowd) {
     SfwBatchDev W = B;
     W.share.mode = 0;
-    CK(c, sfw_launch_crowd(W, reinterpret_cast<unsigned int *>(c->out.dev + c->off_work), c->plan.grid,
+    CK(c, sfw_launch_crowd(W, reinterpret_cast<unsigned int *>(c->out.dev + c->off_work), c->plan.grid, c->plan.T,
                            c->plan.smem, c->stream, true));
     c->launches += sfw_crowd_fuses_argmin(W) ? 1 : 2; // scorer (+ arg-min)
     c->last_kernel = "sfw_score_crowd";
@@ -1783,6 +1811,7 @@ uint64_t sfw_d2h_bytes(const sfw_ctx *c) {
   return (c && c->staged) ? (sizeof(SfwBest) + 4ull * c->out_samples) * c->B.n_scenes : 0;
 }
 const char *sfw_last_kernel(const sfw_ctx *c) { return c ? c->last_kernel : "none"; }
+uint32_t sfw_block_threads(const sfw_ctx *c) { return (c && c->staged && c->plan.valid) ? c->plan.T : 0u; }
 double sfw_obstacle_skip_fraction(const sfw_ctx *c) { return (c && c->staged) ? c->obst_skip_frac : 0.0; }
 double sfw_shared_prefix_steps(const sfw_ctx *c) { return (c && c->share_active) ? c->share_mean_s0 : 0.0; }
 

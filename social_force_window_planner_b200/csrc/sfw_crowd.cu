@@ -27,8 +27,9 @@
 
 namespace {
 
-constexpr int kCrowdThreads = SFW_CROWD_THREADS;
-constexpr int kCrowdWarps = kCrowdThreads / 32;
+// Two instantiations: 256 threads (8 warps, two blocks per SM) for crowds, and 128 threads (4 warps, four blocks per
+// SM) for small crowds on grids that would otherwise need a second wave of 256-thread blocks (BASELINE's 21 x 21
+// tick: 441 trajectories are one wave of 592 slots instead of two of 296).  The host picks one per plan.
 // The thread that carries a trajectory's social work: lane 0 of warp 1.  Warp 0 integrates the pairs of a small
 // crowd in phase 2; the robot's terms are reduced beside it, not after it (one warp alone runs a dependent chain at
 // 7+ cycles per instruction: a 5 x 9 tick is nothing but such chains).
@@ -70,18 +71,19 @@ __device__ __forceinline__ void robot_obstacle_sum_warp(const float2 *__restrict
 
 struct CrowdSmem {
   float4 *pos, *vel, *goal, *par, *par2; // [P2]
-  float4 *frc;                           // [kCrowdWarps][P2]
+  float4 *frc;                           // [warps][P2]
   float2 *obs;                           // [M]
   double2 *fp;                           // [F]
   double *rx, *ry, *rth, *rsn, *rcs;     // [S + 1] pose before step s (entry S = final pose)
   float *rvx;                            // [S + 1] robot vx after s updates (float view for the SFM)
   int *fcm;                              // [S] footprint max per step (>= 254: lethal, 1000: off map)
   uint8_t *goalflag;                     // [2 * P2]
-  float *red;                            // [kCrowdWarps][4]
+  float *red;                            // [warps][4]
   int *flags;                            // [0] work item, [1] hit, [2] first bad step
 };
 
-__device__ __forceinline__ CrowdSmem carve(unsigned char *base, uint32_t P2, uint32_t M, uint32_t F, uint32_t S) {
+__device__ __forceinline__ CrowdSmem carve(unsigned char *base, uint32_t P2, uint32_t M, uint32_t F, uint32_t S,
+                                           uint32_t warps) {
   CrowdSmem s;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -94,7 +96,7 @@ __device__ __forceinline__ CrowdSmem carve(unsigned char *base, uint32_t P2, uin
   s.goal = (float4 *)take(16u * P2);
   s.par = (float4 *)take(16u * P2);
   s.par2 = (float4 *)take(16u * P2);
-  s.frc = (float4 *)take(16u * P2 * kCrowdWarps);
+  s.frc = (float4 *)take(16u * P2 * warps);
   s.obs = (float2 *)take(8u * M);
   s.fp = (double2 *)take(16u * F);
   s.rx = (double *)take(8u * (S + 1));
@@ -105,23 +107,23 @@ __device__ __forceinline__ CrowdSmem carve(unsigned char *base, uint32_t P2, uin
   s.rvx = (float *)take(4u * (S + 1));
   s.fcm = (int *)take(4u * S);
   s.goalflag = (uint8_t *)take(2u * P2);
-  s.red = (float *)take(4u * 4u * kCrowdWarps);
+  s.red = (float *)take(4u * 4u * warps);
   s.flags = (int *)take(16);
   return s;
 }
 
 } // namespace
 
-size_t sfw_crowd_smem_bytes(uint32_t P, uint32_t M, uint32_t F, uint32_t S) {
-  const size_t P2 = (P + 1u) / 2u, Mp = sfw_obst_slots(M);
+size_t sfw_crowd_smem_bytes(uint32_t P, uint32_t M, uint32_t F, uint32_t S, uint32_t threads) {
+  const size_t P2 = (P + 1u) / 2u, Mp = sfw_obst_slots(M), warps = threads / 32u;
   auto r = [](size_t b) { return (b + 15u) & ~(size_t)15u; };
-  return 5 * r(16 * P2) + r(16 * P2 * kCrowdWarps) + r(8 * Mp) + r(16 * (size_t)F) + 5 * r(8 * ((size_t)S + 1)) +
-         r(4 * ((size_t)S + 1)) + r(4 * (size_t)S) + r(2 * P2) + r(16 * kCrowdWarps) + 16;
+  return 5 * r(16 * P2) + r(16 * P2 * warps) + r(8 * Mp) + r(16 * (size_t)F) + 5 * r(8 * ((size_t)S + 1)) +
+         r(4 * ((size_t)S + 1)) + r(4 * (size_t)S) + r(2 * P2) + r(16 * warps) + 16;
 }
 
 // ================================================================================================
 // Arg-min of one scene's cost vector with the reference's tie-breaks (sfw_planner.cpp:394-414), by one block
-// of 256 threads.  Called from sfw_argmin_kernel (one block per scene) or, for small batches, from the last block
+// of up to 512 threads.  Called from sfw_argmin_kernel (one block per scene) or, for small batches, from the last block
 // of sfw_score_crowd to finish (the costs then come from other SMs: L2 loads).
 // ================================================================================================
 __device__ __forceinline__ void scene_argmin(const SfwBatchDev &B, uint32_t scene, float *s_c, uint32_t *s_i) {
@@ -130,7 +132,7 @@ __device__ __forceinline__ void scene_argmin(const SfwBatchDev &B, uint32_t scen
   const float *costs = B.costs + (size_t)scene * n;
   float bc = -1.f;
   uint32_t bi = 0u;
-  for (uint32_t i = B.row_begin * n_w + tid; i < B.row_end * n_w; i += 256u) {
+  for (uint32_t i = B.row_begin * n_w + tid; i < B.row_end * n_w; i += blockDim.x) {
     const float c = __ldcg(costs + i);
     if (eligible(c, B.linvels[i / n_w]) && better(c, i, bc, bi, B.linvels, B.angvels, n_w)) {
       bc = c;
@@ -152,8 +154,9 @@ __device__ __forceinline__ void scene_argmin(const SfwBatchDev &B, uint32_t scen
   }
   __syncthreads();
   if (warp == 0) {
-    bc = (lane < 8u) ? s_c[lane] : -1.f;
-    bi = (lane < 8u) ? s_i[lane] : 0u;
+    const uint32_t n_warps = blockDim.x >> 5; // at most 16 (s_c / s_i hold 16 entries)
+    bc = (lane < n_warps) ? s_c[lane] : -1.f;
+    bi = (lane < n_warps) ? s_i[lane] : 0u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float oc = __shfl_xor_sync(0xffffffffu, bc, o);
@@ -182,15 +185,17 @@ __device__ __forceinline__ void scene_argmin(const SfwBatchDev &B, uint32_t scen
 }
 
 __global__ void __launch_bounds__(256) sfw_argmin_kernel(const __grid_constant__ SfwBatchDev B) {
-  __shared__ float s_c[8];
-  __shared__ uint32_t s_i[8];
+  __shared__ float s_c[16];
+  __shared__ uint32_t s_i[16];
   scene_argmin(B, blockIdx.x, s_c, s_i);
 }
 
 // ================================================================================================
-__global__ void __launch_bounds__(SFW_CROWD_THREADS, 2)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS)
 sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict__ work_counter, int fused_argmin) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int kCrowdThreads = THREADS, kCrowdWarps = THREADS / 32;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t n_w = B.n_w;
   // Rollout prefix sharing (SfwShareDev): mode 1 / 2 items are shared paths that write a record per step,
@@ -225,7 +230,7 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
     const SfwSceneDev *__restrict__ scp = B.scenes + scene;
     const uint32_t P2 = scp->n_pairs, M = scp->n_obst, F = scp->n_fp;
     const uint32_t n_groups = scp->n_groups;
-    const CrowdSmem sm = carve(smem_raw, P2, M, F, (uint32_t)S);
+    const CrowdSmem sm = carve(smem_raw, P2, M, F, (uint32_t)S, (uint32_t)kCrowdWarps);
     double v_s, w_s;
     int s0 = 0;                     // first step this item simulates itself
     const uint8_t *rec_in = nullptr; // record it starts from
@@ -921,11 +926,15 @@ sfw_score_crowd(const __grid_constant__ SfwBatchDev B, unsigned int *__restrict_
 }
 
 // ================================================================================================
-cudaError_t sfw_crowd_prepare(size_t smem_bytes, int *blocks_per_sm) {
-  cudaError_t e = cudaFuncSetAttribute(sfw_score_crowd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-  if (e != cudaSuccess)
-    return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, sfw_score_crowd, kCrowdThreads, smem_bytes);
+cudaError_t sfw_crowd_prepare(uint32_t threads, size_t smem_bytes, int *blocks_per_sm) {
+  auto prep = [&](auto kernel) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess)
+      return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, (int)threads, smem_bytes);
+  };
+  return threads == SFW_CROWD_THREADS_SMALL ? prep(sfw_score_crowd<SFW_CROWD_THREADS_SMALL>)
+                                            : prep(sfw_score_crowd<SFW_CROWD_THREADS>);
 }
 
 bool sfw_crowd_fuses_argmin(const SfwBatchDev &B) {
@@ -936,10 +945,13 @@ bool sfw_crowd_fuses_argmin(const SfwBatchDev &B) {
 // `work_counter`: two words that are 0 before the first launch (sfw_upload clears them) — the kernel re-arms them.
 // Small batches (sfw_crowd_fuses_argmin: at most 8192 cost values in at most 64 scenes) are reduced by the kernel's last block, larger ones by
 // sfw_argmin_kernel with one block per scene.
-cudaError_t sfw_launch_crowd(const SfwBatchDev &B, unsigned int *work_counter, uint32_t grid, size_t smem_bytes,
-                             cudaStream_t stream, bool with_argmin) {
+cudaError_t sfw_launch_crowd(const SfwBatchDev &B, unsigned int *work_counter, uint32_t grid, uint32_t threads,
+                             size_t smem_bytes, cudaStream_t stream, bool with_argmin) {
   const bool fused = with_argmin && sfw_crowd_fuses_argmin(B);
-  sfw_score_crowd<<<grid, kCrowdThreads, smem_bytes, stream>>>(B, work_counter, fused ? 1 : 0);
+  if (threads == SFW_CROWD_THREADS_SMALL)
+    sfw_score_crowd<SFW_CROWD_THREADS_SMALL><<<grid, threads, smem_bytes, stream>>>(B, work_counter, fused ? 1 : 0);
+  else
+    sfw_score_crowd<SFW_CROWD_THREADS><<<grid, threads, smem_bytes, stream>>>(B, work_counter, fused ? 1 : 0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || !with_argmin || fused)
     return e;

@@ -18,7 +18,8 @@
 #define SFW_MAX_PEDS_SMALL 64 /* thread-per-trajectory kernel: goal flags live in one 64-bit mask */
 #define SFW_FAR_AWAY 1.0e15f  /* padding pedestrian / obstacle: every force term underflows to exactly 0 */
 #define SFW_MAX_FOOTPRINT 64
-#define SFW_CROWD_THREADS 256  /* block-per-trajectory kernel (sfw_crowd.cu) */
+#define SFW_CROWD_THREADS 256       /* block-per-trajectory kernel (sfw_crowd.cu) */
+#define SFW_CROWD_THREADS_SMALL 128 /* its second instantiation: small crowds, four blocks per SM */
 /* Block-per-trajectory kernel: the whole crowd of one trajectory lives in one block's shared memory, 208 B per
  * pedestrian PAIR (position, velocity, goal, 2 parameter words, 8 per-warp reaction rows) + the rollout arrays:
  * about 2 100 pedestrians at 128 steps on a B200 (227 KB per block).  2048 is the guaranteed limit; between 2048

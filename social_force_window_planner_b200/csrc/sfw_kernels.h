@@ -19,11 +19,12 @@ cudaError_t sfw_launch_warp_paths(const SfwBatchDev &B, const CUtensorMap &tmap,
 cudaError_t sfw_launch_small(const SfwBatchDev &B, const CUtensorMap &tmap, uint32_t T,
                              size_t smem_bytes, cudaStream_t stream, bool dependent = false);
 // block-per-trajectory kernel for dense crowds (sfw_crowd.cu) + stand-alone arg-min
-size_t sfw_crowd_smem_bytes(uint32_t P, uint32_t M, uint32_t F, uint32_t S);
-cudaError_t sfw_crowd_prepare(size_t smem_bytes, int *blocks_per_sm);
+// (threads: SFW_CROWD_THREADS or SFW_CROWD_THREADS_SMALL — the two instantiations of the kernel)
+size_t sfw_crowd_smem_bytes(uint32_t P, uint32_t M, uint32_t F, uint32_t S, uint32_t threads = SFW_CROWD_THREADS);
+cudaError_t sfw_crowd_prepare(uint32_t threads, size_t smem_bytes, int *blocks_per_sm);
 bool sfw_crowd_fuses_argmin(const SfwBatchDev &B); // the scorer's last block reduces the winners itself
-cudaError_t sfw_launch_crowd(const SfwBatchDev &B, unsigned int *work_counter, uint32_t grid, size_t smem_bytes,
-                             cudaStream_t stream, bool with_argmin);
+cudaError_t sfw_launch_crowd(const SfwBatchDev &B, unsigned int *work_counter, uint32_t grid, uint32_t threads,
+                             size_t smem_bytes, cudaStream_t stream, bool with_argmin);
 cudaError_t sfw_launch_export_invalid(const SfwExchangeDev &X, uint32_t n_scenes, cudaStream_t stream); // sfw_exchange.cu
 cudaError_t sfw_launch_points(const SfwBatchDev &B, uint32_t scene, uint32_t idx, uint32_t n_points,
                               double *out_xyz, cudaStream_t stream);

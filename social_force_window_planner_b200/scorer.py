@@ -285,6 +285,11 @@ class Scorer:
         return self._lib.sfw_last_kernel(self._ctx).decode()
 
     @property
+    def block_threads(self) -> int:
+        """Threads per block of the staged batch's launch plan (``sfw_block_threads``)."""
+        return int(self._lib.sfw_block_threads(self._ctx))
+
+    @property
     def obstacle_skip_fraction(self) -> float:
         """Share of (pedestrian, obstacle cluster) combinations out of reach at the start poses of the staged batch."""
         return float(self._lib.sfw_obstacle_skip_fraction(self._ctx))

@@ -281,6 +281,49 @@ def test_crowd_kernel_with_groups(scorer):
     print(st)
 
 
+@pytest.mark.parametrize("n_peds", [0, 1, 5, 7, 20, 33, 64])
+def test_crowd_kernel_small_blocks_parity(n_peds):
+    """The 128-thread instantiation of the block-per-trajectory kernel (chosen when it saves a wave: a 21 x 21 grid
+    is two waves of 256-thread blocks, one of 128-thread blocks): owner layout (up to 3 pairs), spread layout
+    (4 .. 32 pairs), odd crowds, against the oracle; a row slab of the same grid keeps the block size and stays
+    bit-identical."""
+    from social_force_window_planner_b200.scorer import Scorer
+    wl = dataclasses.replace(S.WORKLOADS["C0"], steps=24, n_peds=n_peds)
+    sc = S.make_scene(wl, 2, hazards=n_peds >= 5)
+    p = wl.params()
+    lin, ang = wl.sample_arrays()
+    s = Scorer(0)
+    try:
+        s.set_policy(Scorer.POLICY_LATENCY)
+        costs, best = s.score(p, [sc], lin, ang)
+        assert s.last_kernel == "sfw_score_crowd"
+        assert s.block_threads == 128, s.block_threads
+        print(parity.compare(p, sc, lin, ang, costs[0], best[0]))
+        s.upload(p, [sc], lin, ang)
+        s.set_row_slab(3, 9)  # 126 samples: one wave of either block size
+        s.run()
+        c2, _ = s.download()
+        assert s.block_threads == 128
+        assert np.array_equal(c2[0][3 * len(ang):9 * len(ang)], costs[0][3 * len(ang):9 * len(ang)])
+    finally:
+        s.close()
+
+
+def test_crowd_kernel_small_blocks_with_groups():
+    from social_force_window_planner_b200.scorer import Scorer
+    wl = dataclasses.replace(S.WORKLOADS["C0"], steps=24, n_peds=24)
+    groups = {0: [0, 1, 2, 3], 2: [8, 9, 10], 5: [20, 21]}
+    p, sc, lin, ang = G._grouped(wl, 3, groups)
+    s = Scorer(0)
+    try:
+        s.set_policy(Scorer.POLICY_LATENCY)
+        costs, best = s.score(p, [sc], lin, ang)
+        assert s.last_kernel == "sfw_score_crowd" and s.block_threads == 128
+        print(parity.compare(p, sc, lin, ang, costs[0], best[0]))
+    finally:
+        s.close()
+
+
 # ---- BASELINE.json configs[2..4] at FULL size: size-independent properties + oracle spot checks -------
 def _spot_check(p, sc, lin, ang, costs, picks):
     """A handful of trajectories of a big grid against the oracle's single-trajectory scorer (same two-branch
