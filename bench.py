@@ -676,14 +676,20 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(hd["algo_bytes"]),
-                         "note": "path is FP32/MUFU-issue bound (about 1e5 flop per algorithmic byte); see issue"},
+                         "note": "path is bound by register-file operand bandwidth / MUFU rate (about 1e5 flop per "
+                                 "algorithmic byte); see issue"},
             "issue": {"reference_interaction_evals_per_s": evals_per_s,
                       "mufu_executed_per_s": mufu_per_s, "mufu_peak_per_s": 148 * 16 * f_sm,
                       "mufu_frac": mufu_per_s / (148 * 16 * f_sm),
                       "model": "reference work (SURVEY.md 8d): S*[N(N-1)+(N-1)] pair + S*N*M obstacle evaluations per "
                                "trajectory (all S steps, as the reference computes them); MUFU count: what the kernels "
                                "execute (each unordered pair once, 4 MUFU; obstacle term 2 MUFU; steps taken from a shared "
-                               "path and obstacle clusters skipped by the far-field cutoff are not counted) against 16 MUFU/clk/SM at the sampled SM clock"},
+                               "path and obstacle clusters skipped by the far-field cutoff are not counted) against 16 MUFU/clk/SM at the sampled SM clock",
+                      "binding": "from the ncu source pages of the same kernels (profiles/r2m_c1_loops.txt, DESIGN.md 4.6; not "
+                                 "measured live): the cross-pair loop (42 % of the C1 warp samples) takes 235 cycles per trip "
+                                 "and sub-partition against 218 of register-operand delivery (2 x 32-bit operands per lane "
+                                 "and cycle, scripts/dbg/mix_bench.cu), the obstacle loop (25 %) runs at the MUFU rate, 10 % "
+                                 "of the warp time waits at the final barrier (14 warps sit 4/4/3/3 on the schedulers)"},
             "clocks": ck,
             "winner": {"valid": int(best["valid"]), "index": int(best["index"]),
                        "v": float(best["v"]), "w": float(best["w"]), "cost": float(best["cost"])},
