@@ -11,7 +11,7 @@ st = torch.cuda.Stream()
 s = Scorer(0, st.cuda_stream)
 with torch.cuda.stream(st):
     s.upload(wl.params(), S.make_scenes(wl, 1), *wl.sample_arrays()); s.sync()
-    for n in [int(a) for a in sys.argv[1:]] or [1, 2, 4, 8]:
+    for n in [1] + [int(a) for a in sys.argv[1:] if int(a) != 1] if len(sys.argv) > 1 else [1, 2, 4, 8]:
         rows = wl.n_v // n
         s.set_row_slab(0, rows)
         for _ in range(3): s.run()

@@ -445,24 +445,56 @@ sfw_score_small(const __grid_constant__ SfwBatchDev B, const __grid_constant__ C
           f2 fx = bc2(0.f), fy = bc2(0.f), fm = bc2(0.f);
           f2 FX = bc2(0.f), FY = bc2(0.f);                                        // reactions from earlier pairs
           f2 s0x = bc2(0.f), s0y = bc2(0.f), s1x = bc2(0.f), s1y = bc2(0.f);      // actions on later pairs
-          for (uint32_t j = 0; j < P2; ++j) {
-            const float4 pb = pos[j * T], vb = vel[j * T]; // broadcast
-            if (mine && j != k) {
-              const bool act = j > k; // pair k acts on pair j, or receives the reaction of pair j's action on it
-              const float4 pA = act ? pa : pb, vA = act ? va : vb, pB = act ? pb : pa, vB = act ? vb : va;
+          // Cross-pair forces: the P2 (P2 - 1) / 2 unordered tiles (pair a < pair b) are DEALT over all 32 lanes
+          // — a lane per pair would walk P2 - 1 tiles one after the other, and two thirds of the warp would watch —
+          // each evaluated exactly as the thread-per-trajectory pass evaluates it at iteration a for target b
+          // (a0 <- (b0, b1), a1 <- (b0, b1)); the four packed results go to the warp's share of the (otherwise
+          // unused) force columns, 16 tiles per row.  Lane k then REPLAYS its pair's sums in that pass's order:
+          // the reactions of the pairs before it, the actions on the pairs after it — same operands, same order,
+          // bit-identical records.
+          {
+            const uint32_t lane = tid & 31u, n_tiles = P2 * (P2 - 1u) / 2u;
+            for (uint32_t t = lane; t < n_tiles; t += 32u) {
+              uint32_t a = 0u, rem = t; // tile t = (a, b): row a of the upper triangle holds P2 - 1 - a tiles
+              while (rem >= P2 - 1u - a) {
+                rem -= P2 - 1u - a;
+                ++a;
+              }
+              const uint32_t b = a + 1u + rem;
+              const float4 pA = pos[a * T], vA = vel[a * T], pB = pos[b * T], vB = vel[b * T];
               const f2 BX = mk2(pB.x, pB.y), BY = mk2(pB.z, pB.w);
               const f2 BVX = mk2(vB.x, vB.y), BVY = mk2(vB.z, vB.w);
               f2 hx, hy, gx2, gy2, hm;
               pair_force2<false>(K, bc2(pA.x), bc2(pA.z), bc2(vA.x), bc2(vA.z), BX, BY, BVX, BVY, hx, hy, hm);
               pair_force2<false>(K, bc2(pA.y), bc2(pA.w), bc2(vA.y), bc2(vA.w), BX, BY, BVX, BVY, gx2, gy2, hm);
-              if (act) {
-                s0x = add2(s0x, hx);
-                s0y = add2(s0y, hy);
-                s1x = add2(s1x, gx2);
-                s1y = add2(s1y, gy2);
-              } else {
-                FX = sub2(FX, add2(hx, gx2));
-                FY = sub2(FY, add2(hy, gy2));
+              float4 *slot = frc + (t >> 4) * T + 2u * (t & 15u);
+              float l, h, l2, h2;
+              un2(hx, l, h);
+              un2(hy, l2, h2);
+              slot[0] = make_float4(l, h, l2, h2);
+              un2(gx2, l, h);
+              un2(gy2, l2, h2);
+              slot[1] = make_float4(l, h, l2, h2);
+            }
+            __syncwarp();
+            if (mine) {
+              for (uint32_t j = 0; j < P2; ++j) {
+                if (j == k)
+                  continue;
+                const uint32_t a = j < k ? j : k, b = j < k ? k : j;
+                const uint32_t t = a * P2 - a * (a + 1u) / 2u + (b - a - 1u);
+                const float4 *slot = frc + (t >> 4) * T + 2u * (t & 15u);
+                const float4 h4 = slot[0], g4 = slot[1];
+                const f2 hx = mk2(h4.x, h4.y), hy = mk2(h4.z, h4.w), gx2 = mk2(g4.x, g4.y), gy2 = mk2(g4.z, g4.w);
+                if (j > k) { // pair k acted on pair j
+                  s0x = add2(s0x, hx);
+                  s0y = add2(s0y, hy);
+                  s1x = add2(s1x, gx2);
+                  s1y = add2(s1y, gy2);
+                } else { // the reaction of pair j's action on pair k
+                  FX = sub2(FX, add2(hx, gx2));
+                  FY = sub2(FY, add2(hy, gy2));
+                }
               }
             }
           }
