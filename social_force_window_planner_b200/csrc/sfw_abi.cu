@@ -144,7 +144,7 @@ int make_plan(sfw_ctx *c, uint32_t n_scenes, uint32_t samples, uint32_t P, uint3
     try_small = false;
   // Block-per-trajectory kernel: 256-thread blocks (two per SM), or — a small crowd on a grid of a few waves —
   // 128-thread blocks (four per SM) when that saves waves.  Measured end to end on one wave of 5 x 9 samples
-  // (scripts/lat_variants.sh): a 128-thread block is 1.06 - 1.09 x slower per trajectory up to 5 pedestrians and
+  // (profiles/r2n_block_size_variants.txt): a 128-thread block is 1.06 - 1.09 x slower per trajectory up to 5 pedestrians and
   // 1.25 - 1.32 x at 20 - 40; BASELINE's 21 x 21 / 5-pedestrian tick goes from two waves to one: 0.100 -> 0.066 ms.
   uint32_t crowd_T = crowd_threads ? crowd_threads : (uint32_t)SFW_CROWD_THREADS;
   size_t crowd_smem = sfw_crowd_smem_bytes(P, M, F, (uint32_t)steps, crowd_T);
