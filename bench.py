@@ -25,6 +25,8 @@ EXTRA LEGS in the same JSON line (``--no-extras`` drops them), each at the size 
   c4  configs[4]: ONE scene, 1024x1024 samples, linvel rows split into N slabs, slab winners merged on the device
       by the exchange's wait kernel (verified against the full-grid winner) — strong scaling
   c2  configs[2] (N = 1 only): 128x128 samples, 128 steps, 500 pedestrians, full grid, + its CPU baseline
+  c0  configs[0] (N = 1 only): the reference's own tick (21x21 samples, 20 steps, 5 pedestrians), device + end to end,
+      + the reference on one core over the whole grid
 
 ``cpu_baseline`` / ``--impl reference``: the reference's own sources (oracle/_ref, compiled unmodified) on the
 box's host cores on a bounded sub-grid of the same scene — all cores, and ONE core ("as shipped": the reference has
@@ -544,6 +546,53 @@ def leg_c2(rig, cpu):
     return out
 
 
+def leg_c0(rig, cpu):
+    """BASELINE configs[0] on one GPU: the reference's own CPU-sized tick (21x21 samples, 20 steps, 5 pedestrians),
+    device-resident and end to end through ``sfw_score``, next to the reference on ONE core (how it ships)."""
+    from social_force_window_planner_b200 import scenes as S
+    from social_force_window_planner_b200._abi import SceneArray
+    wl = S.WORKLOADS["C0"]
+    params = wl.params()
+    lin, ang = wl.sample_arrays()
+    scene = S.make_scene(wl, 0)
+    sc = rig.scorer(1)
+    with rig.torch.cuda.stream(rig.stream):
+        sc.upload(params, [scene], lin, ang)
+        sc.sync()
+    step_ms, kern_ms, _ = rig.timed_ticks(50, 5, sc.run)
+    with rig.torch.cuda.stream(rig.stream):
+        costs, best = sc.download()
+        host = SceneArray([scene])
+        bufs = None
+        for _ in range(5):
+            bufs = sc.score(params, host, lin, ang, want_costs=True, out=bufs)
+        ts = []
+        for _ in range(200):
+            t0 = time.perf_counter()
+            c2, b2 = bufs = sc.score(params, host, lin, ang, want_costs=True, out=bufs)
+            ts.append(time.perf_counter() - t0)
+    assert np.array_equal(c2, costs) and b2[0] == best[0]
+    e2e_ms = statistics.median(ts) * 1e3
+    out = {"workload": f"C0: {wl.n_v}x{wl.n_w} samples, {wl.steps} steps, {wl.n_peds} pedestrians, "
+                       f"{wl.map_w}x{wl.map_h} costmap — one computeVelocityCommands tick",
+           "value": wl.samples / (statistics.mean(step_ms) * 1e-3), "unit": UNIT,
+           "ms_per_step": statistics.mean(step_ms), "kernel": sc.last_kernel, "block_threads": sc.block_threads,
+           "e2e": {"value": wl.samples / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                   "api": "sfw_score (C ABI, host buffers; median of 200 ticks)"}}
+    if cpu is not None:
+        cc = cpu.pop("_costs")
+        cpu.pop("_ri"), cpu.pop("_ci")
+        g = costs[0].astype(np.float64)
+        both = (cc >= 0) & (g >= 0)
+        cpu["ms_per_tick"] = wl.samples / cpu["value"] * 1e3
+        cpu["max_rel_err_vs_gpu"] = float(np.max(np.abs(g[both] - cc[both]) / np.abs(cc[both]))) if both.any() else 0.0
+        cpu["validity_equal"] = bool(np.array_equal(cc >= 0, g >= 0))
+        out["cpu_baseline_1core"] = cpu
+    rig.quiesce()
+    sc.close()
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -575,12 +624,13 @@ def main():
     extras = not args.no_extras
 
     # ---- CPU baseline legs first (rank 0, N = 1 only): fork pools before CUDA is initialised ----------
-    cpu = cpu1 = cpu_c2 = None
+    cpu = cpu1 = cpu_c2 = cpu_c0 = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_rate(args.workload, args.cpu_rows, args.cpu_cols, want_costs=True)
         cpu1 = cpu_rate(args.workload, 2, 48, cores=1)
         if extras:
             cpu_c2 = cpu_rate("C2", 4, 8, want_costs=True)
+            cpu_c0 = cpu_rate("C0", 21, 21, cores=1, want_costs=True)  # the whole tick, on the one core it ships for
 
     import torch
     if not torch.cuda.is_available():
@@ -606,6 +656,7 @@ def main():
         extra["c4"] = leg_c4(rig, k2, 3)
         if world == 1:
             extra["c2"] = leg_c2(rig, cpu_c2)
+            extra["c0"] = leg_c0(rig, cpu_c0)
 
     traj_per_step = wl.samples * world
     value = traj_per_step * args.steps / (hd["total_ms"] * 1e-3)
